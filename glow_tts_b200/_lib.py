@@ -1,0 +1,88 @@
+"""ctypes binding of libglowcore.so (include/glowcore.h).
+
+The product path has no CPU fallback: if the shared library is missing or a
+call fails, a ``GlowCoreError`` is raised -- loudly.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libglowcore.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "glowcore.h")
+
+GLOW_F32, GLOW_I32, GLOW_BF16 = 0, 1, 2
+
+_c = ctypes
+_P, _I, _F, _Z, _U64, _U32 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint64, _c.c_uint32
+
+# name -> (restype, argtypes); kept in step with include/glowcore.h
+# (tests/test_abi.py parses the header and checks every declared symbol is here
+# and exported by the .so).
+SIGNATURES = {
+    "glow_abi_version": (_I, []),
+    "glow_last_error": (_c.c_char_p, []),
+    "glow_launch_count": (_U64, []),
+    "glow_mas_workspace_bytes": (_Z, [_I, _I, _I]),
+    "glow_mas_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _P, _Z, _P]),
+    "glow_mas_forward_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _I]),
+    "glow_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _U32, _U32, _U32, _U32, _I, _P]),
+}
+
+
+class GlowCoreError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libglowcore.so once; fail loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GlowCoreError(
+                "libglowcore.so is not built (%s). Run `python -m glow_tts_b200.csrc.build` "
+                "or __graft_entry__.build(); there is no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().glow_last_error().decode("utf-8", "replace")
+        raise GlowCoreError("%s failed with code %d: %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise GlowCoreError(
+            "%s must live on a CUDA device: glow_tts_b200 runs only on the sm_100a kernels "
+            "in libglowcore.so (no CPU fallback)" % name)
+
+
+def launch_count():
+    return int(lib().glow_launch_count())
+
+
+def header_symbols():
+    """Function names declared in include/glowcore.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(glow_[a-z0-9_]+)\s*\(", text)))

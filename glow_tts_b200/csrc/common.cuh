@@ -1,0 +1,50 @@
+// common.cuh -- shared plumbing for libglowcore.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/glowcore.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libglowcore is written for sm_100a (B200) only"
+#endif
+
+namespace glow {
+
+// thread-local last-error text (glow_last_error)
+char *err_buf();
+int   fail(int code, const char *fmt, ...);
+void  count_launch(int n = 1);
+
+#define GLOW_CHECK_CUDA(expr)                                                        \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess)                                                       \
+            return ::glow::fail(GLOW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,      \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);         \
+    } while (0)
+
+#define GLOW_CHECK_LAUNCH(name)                                                      \
+    do {                                                                             \
+        cudaError_t _e = cudaGetLastError();                                         \
+        if (_e != cudaSuccess)                                                       \
+            return ::glow::fail(GLOW_ERR_CUDA, "launch of %s failed: %s", name,      \
+                                cudaGetErrorString(_e));                             \
+        ::glow::count_launch();                                                      \
+    } while (0)
+
+#define GLOW_REQUIRE(cond, code, ...)                                                \
+    do {                                                                             \
+        if (!(cond)) return ::glow::fail(code, __VA_ARGS__);                         \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;   // B200
+
+}  // namespace glow

@@ -18,6 +18,27 @@ GLOW_F32, GLOW_I32, GLOW_BF16 = 0, 1, 2
 _c = ctypes
 _P, _I, _F, _Z, _U64, _U32 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint64, _c.c_uint32
 
+class FlowConfig(ctypes.Structure):          # glow_flow_config
+    _fields_ = [("blocks", _I), ("channels", _I), ("hidden", _I), ("layers", _I), ("kernel", _I),
+                ("split", _I), ("spk_dim", _I), ("dropout", _F)]
+
+
+class FlowCall(ctypes.Structure):            # glow_flow_call
+    _fields_ = [("cfg", FlowConfig), ("precision", _I), ("batch", _I), ("t_max", _I), ("rows_pad", _I),
+                ("training", _I), ("seed", _U64),
+                ("row_utt", _P), ("row_t", _P), ("utt_off", _P), ("utt_len", _P),
+                ("wpack", _P), ("wpack_tc", _P), ("spk", _P),
+                ("ws_f32", _P), ("ws_act", _P), ("bw_f32", _P), ("bw_act", _P), ("stream", _P)]
+
+
+class AttnCall(ctypes.Structure):            # glow_attn_call
+    _fields_ = [("q", _P), ("k", _P), ("v", _P), ("wk", _P), ("wv", _P), ("lengths", _P), ("mask", _P),
+                ("batch", _I), ("heads", _I), ("t", _I), ("head_dim", _I), ("window", _I),
+                ("dropout", _F), ("seed", _U64), ("stream", _P)]
+
+
+_PCFG, _PCALL, _PATTN = ctypes.POINTER(FlowConfig), ctypes.POINTER(FlowCall), ctypes.POINTER(AttnCall)
+
 # name -> (restype, argtypes); kept in step with include/glowcore.h
 # (tests/test_abi.py parses the header and checks every declared symbol is here
 # and exported by the .so).
@@ -28,6 +49,17 @@ SIGNATURES = {
     "glow_mas_workspace_bytes": (_Z, [_I, _I, _I]),
     "glow_mas_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _P, _Z, _P]),
     "glow_mas_forward_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _I]),
+    "glow_flow_param_slots": (_I, [_PCFG]),
+    "glow_flow_wpack_floats": (_Z, [_PCFG]),
+    "glow_flow_wpack_tc_elems": (_Z, [_PCFG]),
+    "glow_flow_workspace_elems": (_I, [_PCFG, _I, _I, _I, ctypes.POINTER(_Z)]),
+    "glow_flow_prepare": (_I, [_PCFG, _P, _P, _I, _P, _P, _P]),
+    "glow_flow_forward": (_I, [_PCALL, _P, _P, _P]),
+    "glow_flow_reverse": (_I, [_PCALL, _P, _P, _F]),
+    "glow_flow_backward": (_I, [_PCALL, _P, _P, _P, _P, _P]),
+    "glow_flow_param_grads": (_I, [_PCFG, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "glow_rpr_attention_forward": (_I, [_PATTN, _P, _P, _P]),
+    "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _U32, _U32, _U32, _U32, _I, _P]),
 }
 

@@ -1,0 +1,291 @@
+// flow_elem.cuh -- row-wise (non-GEMM) kernels of the flow decoder, shared by the
+// fp32 SIMT path and the bf16 tcgen05 path.
+#pragma once
+#include "flow_epilogues.cuh"
+#include "flow_kernels.cuh"
+
+namespace glow {
+
+// ---------------------------------------------------------------------------
+// Squeeze (Modules.py:895-907) + pack: mel [B,80,T] -> rows [rows_pad,160],
+// channel c' = (t mod 2)*80 + c.  With `mix` the first block's ActNorm + 4x4 mix
+// (Modules.py:693,749) are applied on the way (forward); without, rows are raw
+// (reverse direction input, and gradient packing).
+// One CTA = 32 rows; reads are coalesced along time, writes along channels.
+// ---------------------------------------------------------------------------
+template <typename ActT>
+static __global__ void __launch_bounds__(256)
+pack_rows_kernel(const float *__restrict__ mel, int T, RowMap rm, float *__restrict__ Y, ActT *__restrict__ YA,
+                 const float *__restrict__ mix_scale, const float *__restrict__ mix_bias,
+                 const float *__restrict__ mix_w)
+{
+    __shared__ float tile[32][kC + 1];
+    const int row0 = blockIdx.x * 32, tid = threadIdx.x;
+    // element e -> (c, j) with j = 2*r + parity fastest: 80 channels x 64 time slots
+    for (int e = tid; e < kCh * 64; e += 256) {
+        const int c = e >> 6, j = e & 63, r = j >> 1, par = j & 1;
+        const int row = row0 + r;
+        const int b = rm.row_utt[row];
+        float v = 0.f;
+        if (b >= 0) v = mel[((size_t)b * kCh + c) * T + 2 * rm.row_t[row] + par];
+        tile[r][par * kCh + c] = v;
+    }
+    __syncthreads();
+    // one thread per (row, group): 32 rows x 40 groups
+    for (int e = tid; e < 32 * (kC / 4); e += 256) {
+        const int r = e / (kC / 4), g = e % (kC / 4);
+        const int row = row0 + r;
+        const bool m = rm.row_utt[row] >= 0;
+        float in[4], out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) in[i] = tile[r][group_channel(g, i)];
+        if (mix_w != nullptr) {
+            float u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ch = group_channel(g, i);
+                u[i] = mix_bias[ch] + mix_scale[ch] * in[i];
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                out[o] = m ? mix_w[o * 4] * u[0] + mix_w[o * 4 + 1] * u[1] + mix_w[o * 4 + 2] * u[2] + mix_w[o * 4 + 3] * u[3] : 0.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[i] = in[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tile[r][group_channel(g, i)] = out[i];
+    }
+    __syncthreads();
+    for (int e = tid; e < 32 * kC; e += 256) {
+        const int r = e / kC, ch = e % kC;
+        const float v = tile[r][ch];
+        Y[(size_t)(row0 + r) * kC + ch] = v;
+        if (YA != nullptr && ch < kCh) stf(YA + (size_t)(row0 + r) * kCh + ch, v);
+    }
+}
+
+// Unsqueeze (Modules.py:914-924) + unpack: rows [rows_pad,160] -> out [B,80,T]; every
+// element of `out` is written (zeros / `fill` beyond each utterance's length).
+// grid = (ceil(T/64), B).
+static __global__ void __launch_bounds__(256)
+unpack_rows_kernel(const float *__restrict__ Z, const int32_t *__restrict__ utt_off,
+                   const int32_t *__restrict__ utt_len, int T, float *__restrict__ out, float fill)
+{
+    __shared__ float tile[32][kC + 1];
+    const int b = blockIdx.y, t0 = blockIdx.x * 64, tid = threadIdx.x;
+    const int off = utt_off[b], len = utt_len[b];            // squeezed rows
+    const int r0 = t0 >> 1;
+    for (int e = tid; e < 32 * kC; e += 256) {
+        const int r = e / kC, ch = e % kC;
+        tile[r][ch] = (r0 + r < len) ? Z[(size_t)(off + r0 + r) * kC + ch] : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < kCh * 64; e += 256) {
+        const int c = e >> 6, j = e & 63, t = t0 + j;
+        if (t < T) out[((size_t)b * kCh + c) * T + t] = (t < 2 * len) ? tile[j >> 1][(j & 1) * kCh + c] : fill;
+    }
+}
+
+// logdet[b] = sum of row partials + L_b * sum_k (sum(logs_k) + 40 * logdet(W_k))
+// (Modules.py:694,747,806,309).  One warp per utterance.
+static __global__ void logdet_finish_kernel(const float *__restrict__ rowld, const int32_t *__restrict__ utt_off,
+                                     const int32_t *__restrict__ utt_len, const float *__restrict__ wpack,
+                                     size_t pack_stride, BlockPack bp, int blocks, float *__restrict__ logdet)
+{
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int off = utt_off[b], len = utt_len[b];
+    float s = 0.f;
+    for (int r = lane; r < len; r += 32) s += rowld[off + r];
+    float konst = 0.f;
+    for (int k = 0; k < blocks; ++k) {
+        const float *wp = wpack + (size_t)k * pack_stride;
+        float sl = 0.f;
+        for (int c = lane; c < kC; c += 32) sl += logf(wp[bp.an_scale + c]);
+        konst += sl + (lane == 0 ? (float)(kC / 4) * wp[bp.logdet] : 0.f);
+    }
+    s += konst * (float)len;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) logdet[b] = s;
+}
+
+// Speaker gate bias (Modules.py:863-864): spkb[k][i][b][n'] = W_spk emb[b] + b_spk.
+// grid = (blocks*layers, B), 384 threads.
+static __global__ void spk_bias_kernel(const float *__restrict__ emb, int spk_dim, const float *__restrict__ wpack,
+                                size_t pack_stride, BlockPack bp, int batch, float *__restrict__ spkb)
+{
+    const int kl = blockIdx.x, b = blockIdx.y, n = threadIdx.x;
+    const int k = kl / kLayers, i = kl % kLayers;
+    const float *wp = wpack + (size_t)k * pack_stride;
+    const float *W = wp + bp.spk_w[i];
+    float acc = wp[bp.spk_b[i] + n];
+    for (int d = 0; d < spk_dim; ++d) acc += emb[(size_t)b * spk_dim + d] * W[(size_t)d * kG + n];
+    spkb[((size_t)kl * batch + b) * kG + n] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// Backward of the affine coupling's elementwise part (Modules.py:805-806):
+//   d mean = dz_b ; d logs = dz_b * e^logs * y_b + dlogdet[b] ; d y_b = dz_b * e^logs ; d y_a = dz_a
+// DOUTS is interleaved (d mean, d logs) like OUTS.  One thread per (row, channel pair index c).
+// ---------------------------------------------------------------------------
+template <typename ActT>
+static __global__ void __launch_bounds__(256)
+coupling_bwd_kernel(const float *__restrict__ DZ, const float *__restrict__ Y, const float *__restrict__ OUTS,
+                    const float *__restrict__ dlogdet, const int32_t *__restrict__ row_utt, int rows_pad,
+                    ActT *__restrict__ DOUTS, float *__restrict__ DY)
+{
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= (size_t)rows_pad * kCh) return;
+    const int row = (int)(e / kCh), c = (int)(e % kCh);
+    const int b = row_utt[row];
+    float dmean = 0.f, dlogs = 0.f, dya = 0.f, dyb = 0.f;
+    if (b >= 0) {
+        const float dzb = DZ[(size_t)row * kC + kCh + c];
+        const float es = expf(OUTS[(size_t)row * kC + 2 * c + 1]);
+        const float yb = Y[(size_t)row * kC + kCh + c];
+        dmean = dzb;
+        dlogs = dzb * es * yb + dlogdet[b];
+        dyb = dzb * es;
+        dya = DZ[(size_t)row * kC + c];
+    }
+    stf(DOUTS + (size_t)row * kC + 2 * c, dmean);
+    stf(DOUTS + (size_t)row * kC + 2 * c + 1, dlogs);
+    DY[(size_t)row * kC + c] = dya;
+    DY[(size_t)row * kC + kCh + c] = dyb;
+}
+
+// ---------------------------------------------------------------------------
+// Backward of the 4x4 mix + ActNorm of one block (Modules.py:693,749):
+//   y = W u, u = bias + scale * x   (per group, masked rows)
+//   du = W^T dy ; dW += dy u^T ; dlogs[ch] += du * (u - bias) ; dbias[ch] += du ; dx = du * scale
+// u is recovered as W^-1 y.  DZ receives dx (gradient wrt the previous block's output).
+// One thread per (row, group); per-CTA partial sums go through shared memory, then atomics
+// into the (zeroed) dwpack slots an_scale (dlogs), an_bias, w.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+mix_bwd_kernel(const float *__restrict__ DY, const float *__restrict__ Y, const int32_t *__restrict__ row_utt,
+               int rows_pad, const float *__restrict__ wp, BlockPack bp, float *__restrict__ dwp,
+               float *__restrict__ DZ)
+{
+    __shared__ float s_dlogs[kC], s_dbias[kC], s_dw[16];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kC; i += 256) { s_dlogs[i] = 0.f; s_dbias[i] = 0.f; }
+    if (tid < 16) s_dw[tid] = 0.f;
+    __syncthreads();
+    const float *W = wp + bp.w, *Winv = wp + bp.winv, *scale = wp + bp.an_scale, *bias = wp + bp.an_bias;
+    // CTA covers 32 rows x 40 groups = 1280 items, 5 per thread; consecutive threads -> consecutive groups
+    const int row0 = blockIdx.x * 32;
+    float dw_loc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dw_loc[i] = 0.f;
+    for (int e = tid; e < 32 * (kC / 4); e += 256) {
+        const int r = e / (kC / 4), g = e % (kC / 4);
+        const int row = row0 + r;
+        if (row >= rows_pad) continue;
+        const bool m = row_utt[row] >= 0;
+        float dy[4], y[4], u[4], du[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = group_channel(g, i);
+            dy[i] = m ? DY[(size_t)row * kC + ch] : 0.f;
+            y[i] = Y[(size_t)row * kC + ch];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            u[i] = Winv[i * 4] * y[0] + Winv[i * 4 + 1] * y[1] + Winv[i * 4 + 2] * y[2] + Winv[i * 4 + 3] * y[3];
+            du[i] = W[i] * dy[0] + W[4 + i] * dy[1] + W[8 + i] * dy[2] + W[12 + i] * dy[3];
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dw_loc[o * 4 + i] += dy[o] * u[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = group_channel(g, i);
+            if (m) {
+                atomicAdd(&s_dlogs[ch], du[i] * (u[i] - bias[ch]));
+                atomicAdd(&s_dbias[ch], du[i]);
+            }
+            if (DZ != nullptr) DZ[(size_t)row * kC + ch] = m ? du[i] * scale[ch] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float v = dw_loc[i];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) atomicAdd(&s_dw[i], v);
+    }
+    __syncthreads();
+    for (int i = tid; i < kC; i += 256) {
+        atomicAdd(dwp + bp.an_scale + i, s_dlogs[i]);
+        atomicAdd(dwp + bp.an_bias + i, s_dbias[i]);
+    }
+    if (tid < 16) atomicAdd(dwp + bp.w + tid, s_dw[tid]);
+}
+
+// Column sums over rows: out[n] += sum_row D[row, n]  (bias gradients).  grid = (ceil(N/32), row splits)
+template <typename T>
+static __global__ void __launch_bounds__(256)
+colsum_kernel(const T *__restrict__ D, int ld, int rows, int N, float *__restrict__ out)
+{
+    __shared__ float s[8][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float acc = 0.f;
+    if (n < N)
+        for (int r = r0 + ry; r < r1; r += 8) acc += ldf(D + (size_t)r * ld + n);
+    s[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
+        atomicAdd(out + n, t);
+    }
+}
+
+// Per-utterance column sums: out[b][n] = sum_{rows of b} D[row, n]  (speaker-bias gradient).
+// grid = (ceil(N/128), B), 128 threads.
+template <typename T>
+static __global__ void __launch_bounds__(128)
+seg_colsum_kernel(const T *__restrict__ D, int ld, int N, const int32_t *__restrict__ utt_off,
+                  const int32_t *__restrict__ utt_len, float *__restrict__ out)
+{
+    const int n = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+    if (n >= N) return;
+    const int off = utt_off[b], len = utt_len[b];
+    float acc = 0.f;
+    for (int r = 0; r < len; ++r) acc += ldf(D + (size_t)(off + r) * ld + n);
+    out[(size_t)b * N + n] = acc;
+}
+
+// Speaker conditioning backward for one (block, layer):
+//   dW_spk[d][n'] (+)= sum_b emb[b][d] * dspkb[b][n'] ; db_spk[n'] = sum_b dspkb[b][n'] ;
+//   demb[b][d] += sum_n' dspkb[b][n'] * W_spk[d][n']
+static __global__ void spk_bwd_kernel(const float *__restrict__ emb, int spk_dim, int batch,
+                               const float *__restrict__ dspkb, const float *__restrict__ Wspk,
+                               float *__restrict__ dWspk, float *__restrict__ dbspk, float *__restrict__ demb)
+{
+    const int d = blockIdx.x, tid = threadIdx.x;     // grid = spk_dim, 384 threads
+    for (int n = tid; n < kG; n += blockDim.x) {
+        float acc = 0.f, accb = 0.f;
+        for (int b = 0; b < batch; ++b) {
+            const float g = dspkb[(size_t)b * kG + n];
+            acc += emb[(size_t)b * spk_dim + d] * g;
+            accb += g;
+        }
+        dWspk[(size_t)d * kG + n] = acc;
+        if (d == 0) dbspk[n] = accb;
+    }
+    if (demb != nullptr) {
+        for (int b = 0; b < batch; ++b) {
+            float acc = 0.f;
+            for (int n = tid; n < kG; n += blockDim.x) acc += dspkb[(size_t)b * kG + n] * Wspk[(size_t)d * kG + n];
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((tid & 31) == 0) atomicAdd(demb + (size_t)b * spk_dim + d, acc);
+        }
+    }
+}
+
+}  // namespace glow

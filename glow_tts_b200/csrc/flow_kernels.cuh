@@ -1,0 +1,83 @@
+// flow_kernels.cuh -- internal interface between the flow decoder's host
+// orchestration (flow_host.cu) and its kernels.
+#pragma once
+#include "flow_layout.cuh"
+
+namespace glow {
+
+constexpr int kMaxBlocks = 12;
+constexpr int kMaxWnJobs = kMaxBlocks * (2 + 3 * kLayers);
+
+// ---- weight-norm pack / grad jobs (one CTA per output channel, all tensors in one launch)
+struct WnJob {
+    const float *v, *g, *bias;       // reference parameters (g == null: plain conv)
+    float *W, *WT, *bpack;           // packed effective weights (fp32)
+    __nv_bfloat16 *slabW, *slabWT;   // bf16 slab images (null in fp32 mode)
+    const float *dW, *dbpack;        // grads of effective weights (grad job)
+    float *dv, *dg, *db;             // flat-gradient destinations (grad job)
+    int n_out, k_in, taps, interleave;
+    int cta_begin;
+};
+struct WnJobs {
+    int count, total_ctas;
+    WnJob job[kMaxWnJobs];
+};
+struct SmallJobs {                   // ActNorm + 4x4 conv of every block
+    int blocks, batch;
+    const float *logs[kMaxBlocks], *bias[kMaxBlocks], *w[kMaxBlocks];
+    float *dlogs[kMaxBlocks], *dbias[kMaxBlocks], *dw[kMaxBlocks];
+};
+
+int launch_wn_pack(const WnJobs &jobs, cudaStream_t st);
+int launch_wn_grad(const WnJobs &jobs, cudaStream_t st);
+int launch_block_small(const SmallJobs &jobs, float *wpack, size_t pack_stride, const BlockPack &bp, cudaStream_t st);
+int launch_small_grad(const SmallJobs &jobs, const float *wpack, const float *dwpack, size_t pack_stride,
+                      const BlockPack &bp, const float *dlogdet, const int32_t *utt_len, cudaStream_t st);
+
+// ---- row maps
+struct RowMap {
+    const int32_t *row_utt;   // [rows_pad] utterance id or -1
+    const int32_t *row_t;     // [rows_pad] squeezed frame index inside the utterance
+    const int32_t *utt_off;   // [batch] first row of each utterance
+    const int32_t *utt_len;   // [batch] squeezed frames of each utterance
+    int rows_pad;             // multiple of kRowTile
+    int batch;
+};
+
+// ---- per-step context handed to the kernels
+template <typename ActT>
+struct FlowCtx {
+    FlowCfg cfg;
+    RowMap rows;
+    const float *wpack;              // fp32 packed weights, all blocks
+    const __nv_bfloat16 *wpack_tc;   // bf16 slab images (bf16 mode)
+    BlockPack bp;
+    BlockPackTC bt;
+    WorkLayout wl;
+    float *ws_f32;                   // saved fp32 activations
+    ActT *ws_act;                    // saved ActT activations
+    float *bw_f32;                   // backward scratch
+    ActT *bw_act;
+    const float *spk;                // [B, spk_dim] or null
+    uint64_t seed;                   // 0: no dropout (eval)
+    bool training;                   // keep per-block activations
+    cudaStream_t st;
+};
+
+// forward / reverse / backward over all blocks, fp32 CUDA-core path (flow_simt.cu)
+int flow_forward_f32(const FlowCtx<float> &c, const float *mel, int T, float *z, float *logdet);
+int flow_reverse_f32(const FlowCtx<float> &c, const float *z, int T, float *mel, float fill);
+int flow_backward_f32(const FlowCtx<float> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
+                      float *dmel, float *dspk);
+// bf16 tcgen05 path (flow_tc.cu)
+int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet);
+int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill);
+int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
+                       float *dmel, float *dspk);
+
+// cuBLAS weight-gradient GEMMs (flow_wgrad.cu), row-major:
+//   C[b][K][N] (ldc) = beta*C + A_b[rows,K]^T * D[rows,N],  A_b = A + b*strideA, C_b = C + b*strideC
+int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta);
+
+}  // namespace glow

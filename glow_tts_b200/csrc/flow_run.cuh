@@ -1,0 +1,296 @@
+// flow_run.cuh -- block-by-block orchestration of the flow decoder
+// (Modules.py:298-309 Decoder.forward, :662-668 AIA.forward) over packed rows.
+// Templated on the activation type and on an `Ops` policy that provides the
+// GEMM-shaped steps (SimtOps: fp32 CUDA cores; TcOps: bf16 tcgen05).
+#pragma once
+#include "flow_elem.cuh"
+#include "flow_simt.cuh"
+
+namespace glow {
+
+template <typename ActT>
+struct Bufs {                 // resolved pointers for one block
+    float *Y, *OUTS;
+    ActT *YA, *H[kLayers], *TS[kLayers], *ACTS[kLayers], *OUT;
+};
+
+template <typename ActT>
+inline Bufs<ActT> block_bufs(const FlowCtx<ActT> &c, int k)
+{
+    const size_t R = (size_t)c.rows.rows_pad;
+    const size_t kb = c.training ? (size_t)k : 0;
+    Bufs<ActT> b;
+    b.Y = c.ws_f32 + c.wl.y + kb * R * kC;
+    b.OUTS = c.ws_f32 + c.wl.outs + kb * R * kC;
+    b.YA = c.ws_act + c.wl.ya + kb * R * kCh;
+    for (int i = 0; i < kLayers; ++i) {
+        b.H[i] = c.ws_act + c.wl.h + (kb * kLayers + i) * R * kH;
+        b.TS[i] = c.ws_act + c.wl.ts + (kb * kLayers + i) * R * kG;
+        b.ACTS[i] = c.ws_act + c.wl.acts + (kb * kLayers + i) * R * kH;
+    }
+    b.OUT = c.ws_act + c.wl.out + kb * R * kH;
+    return b;
+}
+
+template <typename ActT>
+inline DropCfg drop_cfg(const FlowCtx<ActT> &c, int k, int i)
+{
+    DropCfg d;
+    d.seed = (c.cfg.dropout > 0.f) ? c.seed : 0;
+    d.base = ((uint64_t)k * kLayers + i) * (uint64_t)c.rows.rows_pad;
+    d.p = c.cfg.dropout;
+    d.inv_keep = 1.f / (1.f - c.cfg.dropout);
+    return d;
+}
+
+template <typename ActT>
+inline const float *spkb_ptr(const FlowCtx<ActT> &c, int k, int i)
+{
+    if (c.spk == nullptr) return nullptr;
+    return c.ws_f32 + c.wl.spkb + ((size_t)k * kLayers + i) * c.rows.batch * kG;
+}
+
+// ------------------------------------------------------------------ SIMT ops --
+template <typename ActT, bool FAST>
+struct SimtOps {
+    using Ctx = FlowCtx<ActT>;
+    static const float *wp(const Ctx &c, int k) { return c.wpack + (size_t)k * c.bp.total; }
+
+    static int start(const Ctx &c, int k, const Bufs<ActT> &b)
+    {
+        ARows<float> a{b.Y, kC};
+        EpiStart<ActT> e{wp(c, k) + c.bp.start_b, b.H[0], c.rows.row_utt};
+        return gemm_simt(a, wp(c, k) + c.bp.start_w, kCh, kH, c.rows.rows_pad, e, c.st, "start");
+    }
+    static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
+    {
+        const bool last = i == kLayers - 1;
+        ATaps<ActT> a{b.H[i], kH, kH, +1, c.rows.rows_pad};
+        EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
+                               drop_cfg(c, k, i)};
+        int rc = gemm_simt(a, wp(c, k) + c.bp.in_w[i], kTaps * kH, kG, c.rows.rows_pad, eg, c.st, "in_gate");
+        if (rc) return rc;
+        ARows<ActT> a2{b.ACTS[i], kH};
+        EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
+                            c.rows.row_utt, i == 0, last};
+        return gemm_simt(a2, wp(c, k) + c.bp.rs_w[i], kH, last ? kH : kG, c.rows.rows_pad, er, c.st, "res_skip");
+    }
+    static int end(const Ctx &c, int k, const Bufs<ActT> &b, const EpiEnd<ActT, FAST> &e)
+    {
+        ARows<ActT> a{b.OUT, kH};
+        return gemm_simt(a, wp(c, k) + c.bp.end_w, kH, kC, c.rows.rows_pad, e, c.st, "end");
+    }
+    // backward
+    static int b_end(const Ctx &c, int k, const ActT *DOUTS, ActT *DOUT)
+    {
+        ARows<ActT> a{DOUTS, kC};
+        EpiBwdEnd<ActT> e{DOUT, c.rows.row_utt};
+        return gemm_simt(a, wp(c, k) + c.bp.end_wt, kC, kH, c.rows.rows_pad, e, c.st, "b_end");
+    }
+    static int b_rs(const Ctx &c, int k, int i, const Bufs<ActT> &b, const ActT *DHnext, const ActT *DOUT,
+                    ActT *DINS, ActT *DPRE)
+    {
+        EpiBwdGate<ActT> e{b.TS[i], DINS, DPRE, c.rows.row_utt, drop_cfg(c, k, i)};
+        if (i == kLayers - 1) {
+            ARows<ActT> a{DOUT, kH};
+            return gemm_simt(a, wp(c, k) + c.bp.rs_wt[i], kH, kH, c.rows.rows_pad, e, c.st, "b_rs");
+        }
+        AConcat<ActT> a{DHnext, DOUT, kH, kH, kH};
+        return gemm_simt(a, wp(c, k) + c.bp.rs_wt[i], kG, kH, c.rows.rows_pad, e, c.st, "b_rs");
+    }
+    static int b_in(const Ctx &c, int k, int i, const ActT *DPRE, const ActT *DHnext, ActT *DH)
+    {
+        ATaps<ActT> a{DPRE, kG, kG, -1, c.rows.rows_pad};
+        EpiBwdIn<ActT> e{DHnext, DH, c.rows.row_utt};
+        return gemm_simt(a, wp(c, k) + c.bp.in_wt[i], kTaps * kG, kH, c.rows.rows_pad, e, c.st, "b_in");
+    }
+    static int b_start(const Ctx &c, int k, const ActT *DH0, float *DY)
+    {
+        ARows<ActT> a{DH0, kH};
+        EpiBwdStart e{DY};
+        return gemm_simt(a, wp(c, k) + c.bp.start_wt, kH, kCh, c.rows.rows_pad, e, c.st, "b_start");
+    }
+};
+
+#define GLOW_TRY(expr)            \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != GLOW_OK) return _rc; \
+    } while (0)
+
+// ------------------------------------------------------------- forward -------
+template <typename ActT, bool FAST, class Ops>
+int flow_forward_impl(const FlowCtx<ActT> &c, const float *mel, int T, float *z, float *logdet)
+{
+    const int R = c.rows.rows_pad, B = c.rows.batch;
+    float *rowld = c.ws_f32 + c.wl.rowld;
+    float *SKIP = c.ws_f32 + c.wl.skip;
+    float *Zfinal = c.ws_f32 + c.wl.zfinal;
+    GLOW_CHECK_CUDA(cudaMemsetAsync(rowld, 0, sizeof(float) * R, c.st));
+    if (c.spk != nullptr) {
+        spk_bias_kernel<<<dim3(c.cfg.blocks * kLayers, B), kG, 0, c.st>>>(c.spk, c.cfg.spk_dim, c.wpack, c.bp.total,
+                                                                         c.bp, B, c.ws_f32 + c.wl.spkb);
+        GLOW_CHECK_LAUNCH("spk_bias_kernel");
+    }
+    {
+        Bufs<ActT> b0 = block_bufs(c, 0);
+        const float *wp0 = c.wpack;
+        pack_rows_kernel<ActT><<<R / 32, 256, 0, c.st>>>(mel, T, c.rows, b0.Y, b0.YA, wp0 + c.bp.an_scale,
+                                                        wp0 + c.bp.an_bias, wp0 + c.bp.w);
+        GLOW_CHECK_LAUNCH("pack_rows_kernel");
+    }
+    for (int k = 0; k < c.cfg.blocks; ++k) {
+        Bufs<ActT> b = block_bufs(c, k);
+        GLOW_TRY(Ops::start(c, k, b));
+        for (int i = 0; i < kLayers; ++i) GLOW_TRY(Ops::layer(c, k, i, b, SKIP));
+        const bool has_next = k + 1 < c.cfg.blocks;
+        Bufs<ActT> bn = block_bufs(c, has_next ? k + 1 : k);
+        const float *wpn = c.wpack + (size_t)(k + 1) * c.bp.total;
+        EpiEnd<ActT, FAST> e;
+        e.bias = c.wpack + (size_t)k * c.bp.total + c.bp.end_b;
+        e.Y = b.Y;
+        e.OUTS = c.training ? b.OUTS : nullptr;
+        e.rowld = rowld;
+        e.Ynext = has_next ? bn.Y : Zfinal;
+        e.YAnext = has_next ? bn.YA : nullptr;
+        e.mix_scale = has_next ? wpn + c.bp.an_scale : nullptr;
+        e.mix_bias = has_next ? wpn + c.bp.an_bias : nullptr;
+        e.mix_w = has_next ? wpn + c.bp.w : nullptr;
+        e.row_utt = c.rows.row_utt;
+        e.reverse = 0;
+        GLOW_TRY(Ops::end(c, k, b, e));
+    }
+    unpack_rows_kernel<<<dim3((T + 63) / 64, B), 256, 0, c.st>>>(Zfinal, c.rows.utt_off, c.rows.utt_len, T, z, 0.f);
+    GLOW_CHECK_LAUNCH("unpack_rows_kernel");
+    logdet_finish_kernel<<<B, 32, 0, c.st>>>(rowld, c.rows.utt_off, c.rows.utt_len, c.wpack, c.bp.total, c.bp,
+                                            c.cfg.blocks, logdet);
+    GLOW_CHECK_LAUNCH("logdet_finish_kernel");
+    return GLOW_OK;
+}
+
+// ------------------------------------------------------------- reverse -------
+// Modules.py:303,664: blocks 11..0, inside a block coupling^-1 -> mix^-1 -> ActNorm^-1.
+template <typename ActT, bool FAST, class Ops>
+int flow_reverse_impl(const FlowCtx<ActT> &c, const float *z, int T, float *mel, float fill)
+{
+    const int R = c.rows.rows_pad, B = c.rows.batch;
+    float *SKIP = c.ws_f32 + c.wl.skip;
+    if (c.spk != nullptr) {
+        spk_bias_kernel<<<dim3(c.cfg.blocks * kLayers, B), kG, 0, c.st>>>(c.spk, c.cfg.spk_dim, c.wpack, c.bp.total,
+                                                                         c.bp, B, c.ws_f32 + c.wl.spkb);
+        GLOW_CHECK_LAUNCH("spk_bias_kernel");
+    }
+    Bufs<ActT> b = block_bufs(c, 0);          // inference: one block's worth of buffers, updated in place
+    pack_rows_kernel<ActT><<<R / 32, 256, 0, c.st>>>(z, T, c.rows, b.Y, b.YA, nullptr, nullptr, nullptr);
+    GLOW_CHECK_LAUNCH("pack_rows_kernel");
+    for (int k = c.cfg.blocks - 1; k >= 0; --k) {
+        const float *wpk = c.wpack + (size_t)k * c.bp.total;
+        GLOW_TRY(Ops::start(c, k, b));
+        for (int i = 0; i < kLayers; ++i) GLOW_TRY(Ops::layer(c, k, i, b, SKIP));
+        EpiEnd<ActT, FAST> e;
+        e.bias = wpk + c.bp.end_b;
+        e.Y = b.Y;
+        e.OUTS = nullptr;
+        e.rowld = nullptr;
+        e.Ynext = b.Y;                        // same thread reads and writes the same 4 channels of a row
+        e.YAnext = b.YA;
+        e.mix_scale = wpk + c.bp.an_scale;
+        e.mix_bias = wpk + c.bp.an_bias;
+        e.mix_w = wpk + c.bp.winv;
+        e.row_utt = c.rows.row_utt;
+        e.reverse = 1;
+        GLOW_TRY(Ops::end(c, k, b, e));
+    }
+    unpack_rows_kernel<<<dim3((T + 63) / 64, B), 256, 0, c.st>>>(b.Y, c.rows.utt_off, c.rows.utt_len, T, mel, fill);
+    GLOW_CHECK_LAUNCH("unpack_rows_kernel");
+    return GLOW_OK;
+}
+
+// ------------------------------------------------------------- backward ------
+template <typename ActT, bool FAST, class Ops>
+int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
+                       float *dmel, float *dspk)
+{
+    const int R = c.rows.rows_pad, B = c.rows.batch;
+    constexpr bool kBf16 = sizeof(ActT) == 2;
+    float *DZ = c.bw_f32 + c.wl.dz, *DY = c.bw_f32 + c.wl.dy;
+    ActT *DOUTS = c.bw_act + c.wl.douts, *DOUT = c.bw_act + c.wl.dout;
+    ActT *DHb[2] = {c.bw_act + c.wl.dh[0], c.bw_act + c.wl.dh[1]};
+    ActT *DINS = c.bw_act + c.wl.dins;
+    const bool drop_on = c.cfg.dropout > 0.f && c.seed != 0;
+    ActT *DPRE = drop_on ? c.bw_act + c.wl.dpre : DINS;
+    GLOW_CHECK_CUDA(cudaMemsetAsync(dwpack, 0, sizeof(float) * c.bp.total * c.cfg.blocks, c.st));
+    pack_rows_kernel<float><<<R / 32, 256, 0, c.st>>>(dz, T, c.rows, DZ, (float *)nullptr, nullptr, nullptr, nullptr);
+    GLOW_CHECK_LAUNCH("pack_rows_kernel");
+    const int G2 = kGuard;                       // wgrad GEMMs skip the leading/trailing guard rows
+    const int Rw = R - 2 * G2;
+    for (int k = c.cfg.blocks - 1; k >= 0; --k) {
+        Bufs<ActT> b = block_bufs(c, k);
+        float *dwp = dwpack + (size_t)k * c.bp.total;
+        const size_t n_el = (size_t)R * kCh;
+        coupling_bwd_kernel<ActT><<<(unsigned)((n_el + 255) / 256), 256, 0, c.st>>>(DZ, b.Y, b.OUTS, dlogdet,
+                                                                                   c.rows.row_utt, R, DOUTS, DY);
+        GLOW_CHECK_LAUNCH("coupling_bwd_kernel");
+        GLOW_TRY(Ops::b_end(c, k, DOUTS, DOUT));
+        // dW_end[192][160] = OUT^T DOUTS ; db_end
+        GLOW_TRY(wgrad_gemm(c.st, kBf16, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f));
+        colsum_kernel<ActT><<<dim3(kC / 32, 32), 256, 0, c.st>>>(DOUTS, kC, R, kC, dwp + c.bp.end_b);
+        GLOW_CHECK_LAUNCH("colsum_kernel");
+        const ActT *DHnext = nullptr;
+        for (int i = kLayers - 1; i >= 0; --i) {
+            const bool last = i == kLayers - 1;
+            const int rs_n = last ? kH : kG;
+            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, DINS, DPRE));
+            // dW_rs[192][rs_n]: res columns from d(h_{i+1}), skip columns from d(out)
+            if (!last) {
+                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DHnext, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
+                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f));
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DHnext, kH, R, kH, dwp + c.bp.rs_b[i]);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i] + kH);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+            } else {
+                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i]);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+            }
+            if (c.spk != nullptr) {
+                float *dspkb = c.bw_f32 + c.wl.dspkb;
+                seg_colsum_kernel<ActT><<<dim3(kG / 128, B), 128, 0, c.st>>>(DINS, kG, kG, c.rows.utt_off,
+                                                                            c.rows.utt_len, dspkb);
+                GLOW_CHECK_LAUNCH("seg_colsum_kernel");
+                spk_bwd_kernel<<<c.cfg.spk_dim, 128, 0, c.st>>>(c.spk, c.cfg.spk_dim, B, dspkb,
+                                                               c.wpack + (size_t)k * c.bp.total + c.bp.spk_w[i],
+                                                               dwp + c.bp.spk_w[i], dwp + c.bp.spk_b[i], dspk);
+                GLOW_CHECK_LAUNCH("spk_bwd_kernel");
+            }
+            ActT *DH = DHb[i & 1];
+            GLOW_TRY(Ops::b_in(c, k, i, DPRE, last ? nullptr : DHnext, DH));
+            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
+            GLOW_TRY(wgrad_gemm(c.st, kBf16, b.H[i], kH, DPRE + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
+                                kTaps, kH, (long long)kH * kG, 0.f));
+            colsum_kernel<ActT><<<dim3(kG / 32, 32), 256, 0, c.st>>>(DPRE, kG, R, kG, dwp + c.bp.in_b[i]);
+            GLOW_CHECK_LAUNCH("colsum_kernel");
+            DHnext = DH;
+        }
+        GLOW_TRY(Ops::b_start(c, k, DHnext, DY));
+        if (kBf16) {
+            GLOW_TRY(wgrad_gemm(c.st, true, b.YA, kCh, DHnext, kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
+        } else {
+            GLOW_TRY(wgrad_gemm(c.st, false, b.Y, kC, DHnext, kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
+        }
+        colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DHnext, kH, R, kH, dwp + c.bp.start_b);
+        GLOW_CHECK_LAUNCH("colsum_kernel");
+        const bool need_dz = k > 0 || dmel != nullptr;
+        mix_bwd_kernel<<<R / 32, 256, 0, c.st>>>(DY, b.Y, c.rows.row_utt, R, c.wpack + (size_t)k * c.bp.total, c.bp, dwp,
+                                                need_dz ? DZ : nullptr);
+        GLOW_CHECK_LAUNCH("mix_bwd_kernel");
+    }
+    if (dmel != nullptr) {
+        unpack_rows_kernel<<<dim3((T + 63) / 64, B), 256, 0, c.st>>>(DZ, c.rows.utt_off, c.rows.utt_len, T, dmel, 0.f);
+        GLOW_CHECK_LAUNCH("unpack_rows_kernel");
+    }
+    return GLOW_OK;
+}
+
+}  // namespace glow

@@ -1,0 +1,56 @@
+// flow_wgrad.cu -- weight-gradient GEMMs of the coupling net (reduction over the
+// packed row axis) as plain library GEMMs: cuBLAS, fp32 accumulate.
+//   row-major C[K][N] = A[rows,K]^T D[rows,N]
+//   == column-major C^T (N x K) = D^T(N x rows) * A^T^T ... i.e. gemm(N, T) with
+//   m = N, n = K, k = rows, first operand D (ld = ldd), second operand A (ld = lda).
+#include <cublas_v2.h>
+#include <mutex>
+
+#include "flow_kernels.cuh"
+
+namespace glow {
+
+static std::mutex g_handle_mu;
+static cublasHandle_t g_handles[16] = {nullptr};
+
+static int get_handle(cublasHandle_t *out)
+{
+    int dev = 0;
+    GLOW_CHECK_CUDA(cudaGetDevice(&dev));
+    GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
+    std::lock_guard<std::mutex> lock(g_handle_mu);
+    if (g_handles[dev] == nullptr) {
+        cublasStatus_t s = cublasCreate(&g_handles[dev]);
+        GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasCreate failed: %d", (int)s);
+    }
+    *out = g_handles[dev];
+    return GLOW_OK;
+}
+
+int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta)
+{
+    cublasHandle_t h;
+    int rc = get_handle(&h);
+    if (rc != GLOW_OK) return rc;
+    cublasStatus_t s = cublasSetStream(h, st);
+    GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasSetStream failed: %d", (int)s);
+    const float alpha = 1.f;
+    const cudaDataType_t in_t = bf16 ? CUDA_R_16BF : CUDA_R_32F;
+    const cublasComputeType_t comp = bf16 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_PEDANTIC;
+    if (batch <= 1) {
+        s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, K, rows, &alpha, D, in_t, ldd, A, in_t, lda, &beta, C,
+                         CUDA_R_32F, ldc, comp, CUBLAS_GEMM_DEFAULT);
+    } else {
+        const long long esz_stride_a = strideA;   // in elements of the input type
+        s = cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, K, rows, &alpha, D, in_t, ldd, 0, A, in_t, lda,
+                                       esz_stride_a, &beta, C, CUDA_R_32F, ldc, strideC, batch, comp,
+                                       CUBLAS_GEMM_DEFAULT);
+    }
+    GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasGemm(rows=%d,K=%d,N=%d,batch=%d) failed: %d", rows,
+                 K, N, batch, (int)s);
+    count_launch();
+    return GLOW_OK;
+}
+
+}  // namespace glow

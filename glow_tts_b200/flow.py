@@ -1,0 +1,216 @@
+"""Host side of the flow decoder: packed-row maps, workspaces, the per-step weight
+preparation and the autograd bridge to libglowcore's glow_flow_* entry points
+(include/glowcore.h).  Mirrors what Modules.py:286-309 (Decoder) drives in the
+reference; no arithmetic happens in Python."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+GUARD = 2
+ROW_TILE = 128
+
+
+class RowMap:
+    """Packed row axis for a batch of squeezed lengths (host-built, device-resident)."""
+
+    def __init__(self, sq_lengths, device):
+        lens = np.asarray(sq_lengths, dtype=np.int64)
+        if lens.ndim != 1 or len(lens) == 0 or (lens < 0).any():
+            raise ValueError("squeezed lengths must be a non-empty 1-D array of non-negative ints")
+        b = len(lens)
+        off = np.zeros(b, np.int64)
+        pos = GUARD
+        for i in range(b):
+            off[i] = pos
+            pos += int(lens[i]) + GUARD
+        rows_pad = max(ROW_TILE, (pos + ROW_TILE - 1) // ROW_TILE * ROW_TILE)
+        row_utt = np.full(rows_pad, -1, np.int32)
+        row_t = np.zeros(rows_pad, np.int32)
+        for i in range(b):
+            row_utt[off[i]:off[i] + lens[i]] = i
+            row_t[off[i]:off[i] + lens[i]] = np.arange(lens[i], dtype=np.int32)
+        self.batch, self.rows_pad, self.rows_real = b, int(rows_pad), int(lens.sum())
+        self.lengths = lens
+        packed = np.concatenate([row_utt, row_t, off.astype(np.int32), lens.astype(np.int32)])
+        dev = torch.from_numpy(packed).to(device, non_blocking=True)
+        self.row_utt = dev[:rows_pad]
+        self.row_t = dev[rows_pad:2 * rows_pad]
+        self.utt_off = dev[2 * rows_pad:2 * rows_pad + b]
+        self.utt_len = dev[2 * rows_pad + b:]
+        self._keep = dev
+
+
+_ROWMAP_CACHE = {}
+
+
+def row_map(sq_lengths, device):
+    key = (tuple(int(x) for x in sq_lengths), str(device))
+    rm = _ROWMAP_CACHE.get(key)
+    if rm is None:
+        if len(_ROWMAP_CACHE) > 64:
+            _ROWMAP_CACHE.clear()
+        rm = _ROWMAP_CACHE[key] = RowMap(sq_lengths, device)
+    return rm
+
+
+def precision_tag(precision):
+    if precision in ("fp32", "f32", torch.float32):
+        return _lib.GLOW_F32, torch.float32
+    if precision in ("bf16", torch.bfloat16):
+        return _lib.GLOW_BF16, torch.bfloat16
+    raise ValueError("precision must be 'fp32' or 'bf16', got %r" % (precision,))
+
+
+class FlowPlan:
+    """Everything one decoder call needs besides the tensors: config, flat parameter
+    buffer + offset table, packed weights, workspaces (cached per shape)."""
+
+    def __init__(self, blocks, spk_dim, dropout, channels=160, hidden=192, layers=4, kernel=5, split=4):
+        self.cfg = _lib.FlowConfig(blocks, channels, hidden, layers, kernel, split, spk_dim, dropout)
+        L = _lib.lib()
+        slots = L.glow_flow_param_slots(ctypes.byref(self.cfg))
+        if slots <= 0:
+            _lib.check(slots if slots < 0 else -2, "glow_flow_param_slots")
+        self.slots = slots
+        self.wpack_floats = L.glow_flow_wpack_floats(ctypes.byref(self.cfg))
+        self.wpack_tc_elems = L.glow_flow_wpack_tc_elems(ctypes.byref(self.cfg))
+        self._ws = {}
+        self._wpack = {}
+
+    # -- packed effective weights -------------------------------------------------
+    def wpack(self, device, tag):
+        key = (str(device), tag)
+        if key not in self._wpack:
+            wp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
+            wtc = (torch.empty(self.wpack_tc_elems, dtype=torch.bfloat16, device=device)
+                   if tag == _lib.GLOW_BF16 else None)
+            dwp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
+            self._wpack[key] = (wp, wtc, dwp)
+        return self._wpack[key]
+
+    def prepare(self, flat_params, offsets_host, device, tag):
+        wp, wtc, _ = self.wpack(device, tag)
+        rc = _lib.lib().glow_flow_prepare(ctypes.byref(self.cfg), _lib.ptr(flat_params),
+                                          offsets_host.ctypes.data, tag, _lib.ptr(wp), _lib.ptr(wtc),
+                                          _lib.stream_ptr(device))
+        _lib.check(rc, "glow_flow_prepare")
+        return wp, wtc
+
+    # -- workspaces ------------------------------------------------------------------
+    def workspace(self, rm, device, act_dtype, training):
+        key = (rm.rows_pad, rm.batch, str(device), act_dtype, bool(training))
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            out = (ctypes.c_size_t * 4)()
+            rc = _lib.lib().glow_flow_workspace_elems(ctypes.byref(self.cfg), rm.rows_pad, rm.batch,
+                                                      int(training), out)
+            _lib.check(rc, "glow_flow_workspace_elems")
+            # zero-filled once: guard rows of every buffer must read as finite zeros
+            ws = (torch.zeros(max(out[0], 1), dtype=torch.float32, device=device),
+                  torch.zeros(max(out[1], 1), dtype=act_dtype, device=device),
+                  torch.zeros(max(out[2], 1), dtype=torch.float32, device=device) if training else None,
+                  torch.zeros(max(out[3], 1), dtype=act_dtype, device=device) if training else None)
+            self._ws[key] = ws
+        return ws
+
+    def call_struct(self, rm, t_max, tag, wp, wtc, spk, ws, training, seed, device):
+        c = _lib.FlowCall()
+        c.cfg = self.cfg
+        c.precision, c.batch, c.t_max, c.rows_pad = tag, rm.batch, int(t_max), rm.rows_pad
+        c.training, c.seed = int(training), int(seed) & 0xFFFFFFFFFFFFFFFF
+        c.row_utt, c.row_t = rm.row_utt.data_ptr(), rm.row_t.data_ptr()
+        c.utt_off, c.utt_len = rm.utt_off.data_ptr(), rm.utt_len.data_ptr()
+        c.wpack = wp.data_ptr()
+        c.wpack_tc = wtc.data_ptr() if wtc is not None else None
+        c.spk = spk.data_ptr() if spk is not None else None
+        c.ws_f32, c.ws_act = ws[0].data_ptr(), ws[1].data_ptr()
+        c.bw_f32 = ws[2].data_ptr() if ws[2] is not None else None
+        c.bw_act = ws[3].data_ptr() if ws[3] is not None else None
+        c.stream = torch.cuda.current_stream(device).cuda_stream
+        return c
+
+
+class FlowDecoderFn(torch.autograd.Function):
+    """mel [B,80,T] -> (z [B,80,T], logdet [B]).  `params` are passed only so autograd
+    knows the dependency; the kernels read them through `owner`'s flat buffer."""
+
+    @staticmethod
+    def forward(ctx, owner, rm, mel, spk, seed, *params):
+        plan, device = owner.plan, mel.device
+        tag, act_dtype = precision_tag(owner.precision)
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        flat, offs = owner.flat_params()
+        mel = mel.contiguous().float()
+        spk_c = spk.contiguous().float() if spk is not None else None
+        b, _, t = mel.shape
+        with torch.cuda.device(device):
+            wp, wtc = plan.prepare(flat, offs, device, tag)
+            ws = plan.workspace(rm, device, act_dtype, training)
+            call = plan.call_struct(rm, t, tag, wp, wtc, spk_c, ws, training, seed, device)
+            z = torch.empty_like(mel)
+            logdet = torch.empty(b, dtype=torch.float32, device=device)
+            rc = _lib.lib().glow_flow_forward(ctypes.byref(call), _lib.ptr(mel), _lib.ptr(z), _lib.ptr(logdet))
+        _lib.check(rc, "glow_flow_forward")
+        ctx.owner, ctx.rm, ctx.call, ctx.keep = owner, rm, call, (wp, wtc, ws, spk_c, flat)
+        ctx.need_dmel = mel.requires_grad
+        ctx.has_spk = spk is not None
+        ctx.training = training
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable()
+        return z, logdet
+
+    @staticmethod
+    def backward(ctx, dz, dlogdet):
+        if not ctx.training:
+            raise _lib.GlowCoreError("flow decoder forward ran without grad: no saved activations")
+        owner, rm, call = ctx.owner, ctx.rm, ctx.call
+        plan = owner.plan
+        wp, wtc, ws, spk_c, flat = ctx.keep
+        device = wp.device
+        tag, _ = precision_tag(owner.precision)
+        dz = dz.contiguous().float() if dz is not None else torch.zeros(
+            (rm.batch, 80, call.t_max), dtype=torch.float32, device=device)
+        dlogdet = (dlogdet.contiguous().float() if dlogdet is not None
+                   else torch.zeros(rm.batch, dtype=torch.float32, device=device))
+        _, _, dwp = plan.wpack(device, tag)
+        dmel = torch.empty_like(dz) if ctx.need_dmel else None
+        dspk = torch.empty_like(spk_c) if ctx.has_spk else None
+        _, offs = owner.flat_params()
+        gflat, direct = owner.flat_grads()
+        with torch.cuda.device(device):
+            call.stream = torch.cuda.current_stream(device).cuda_stream
+            rc = _lib.lib().glow_flow_backward(ctypes.byref(call), _lib.ptr(dz), _lib.ptr(dlogdet), _lib.ptr(dwp),
+                                               _lib.ptr(dmel), _lib.ptr(dspk))
+            _lib.check(rc, "glow_flow_backward")
+            rc = _lib.lib().glow_flow_param_grads(ctypes.byref(plan.cfg), _lib.ptr(flat), offs.ctypes.data,
+                                                  _lib.ptr(wp), _lib.ptr(dwp), _lib.ptr(dlogdet),
+                                                  rm.utt_len.data_ptr(), rm.batch, _lib.ptr(gflat),
+                                                  _lib.stream_ptr(device))
+            _lib.check(rc, "glow_flow_param_grads")
+        if direct:        # gradients were accumulated straight into the .grad views
+            pgrads = (None,) * ctx.n_params
+        else:
+            pgrads = owner.split_grads(gflat)
+        return (None, None, dmel, dspk, None) + tuple(pgrads)
+
+
+def flow_reverse(owner, rm, z, spk, fill):
+    """z [B,80,T] -> mel [B,80,T] (Decoder(reverse=True), Modules.py:303,664), no autograd."""
+    plan, device = owner.plan, z.device
+    tag, act_dtype = precision_tag(owner.precision)
+    flat, offs = owner.flat_params()
+    z = z.contiguous().float()
+    spk_c = spk.contiguous().float() if spk is not None else None
+    with torch.cuda.device(device):
+        wp, wtc = plan.prepare(flat, offs, device, tag)
+        ws = plan.workspace(rm, device, act_dtype, False)
+        call = plan.call_struct(rm, z.shape[2], tag, wp, wtc, spk_c, ws, False, 0, device)
+        mel = torch.empty_like(z)
+        rc = _lib.lib().glow_flow_reverse(ctypes.byref(call), _lib.ptr(z), _lib.ptr(mel), ctypes.c_float(fill))
+    _lib.check(rc, "glow_flow_reverse")
+    return mel

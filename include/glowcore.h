@@ -86,6 +86,118 @@ int glow_mas_forward_host(int32_t *paths, const float *values,
                           float max_neg_val, int device);
 
 /* ------------------------------------------------------------------------ *
+ * Flow decoder: Squeeze -> 12 x [ActNorm -> invertible 4x4 channel mix ->
+ * affine coupling (Start 1x1, 4 x (k=5 gated conv, res/skip 1x1), End 1x1)]
+ * -> Unsqueeze, forward (mel -> z, logdet), reverse (z -> mel) and backward.
+ * replaces: Modules.py:298-309 Decoder.forward, :662-668 AIA.forward,
+ *           :682-711 Activation_Norm, :727-758 Invertible_1x1_Conv,
+ *           :780-810 Affine_Coupling_Layer, :858-887 WaveNet,
+ *           :895-924 Squeeze/Unsqueeze, and autograd's backward of all of them.
+ *
+ * Data layout: every utterance's squeezed frames are packed along
+ * one row axis, channels-last, separated by 2 zero guard rows; the caller
+ * passes the row maps:
+ *   row_utt [rows_pad] i32  utterance id of a row, -1 on guard / tail rows
+ *   row_t   [rows_pad] i32  squeezed frame index of the row in its utterance
+ *   utt_off [batch]    i32  first row of each utterance
+ *   utt_len [batch]    i32  squeezed length (mel_length / 2)
+ * rows_pad is a multiple of 128 and rows_pad >= last row + 2.
+ *
+ * Parameters: one flat f32 buffer + a HOST int64 table
+ * offsets[block * glow_flow_param_slots(cfg) + slot] of element offsets, slots
+ * in the reference state_dict order of one block (Modules.py:653-887):
+ *   0 ActNorm.logs[160] 1 ActNorm.bias[160] 2 W[4,4]
+ *   3 Start.bias 4 Start.weight_g 5 Start.weight_v[192,80,1]
+ *   per layer i: In.bias, In.weight_g, In.weight_v[384,192,5],
+ *                Res_Skip.bias, .weight_g, .weight_v[384|192,192,1],
+ *                (spk_dim>0: Speaker.bias, .weight_g, .weight_v[384,spk_dim,1])
+ *   then End.weight[160,192,1], End.bias[160].
+ * Gradients are accumulated (+=) into a second flat buffer at the same offsets.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int   blocks;     /* Decoder.Stack (12) */
+    int   channels;   /* Mel_Dim * Num_Squeeze (160) */
+    int   hidden;     /* Affine_Coupling.Calc_Channels (192) */
+    int   layers;     /* WaveNet.Num_Layers (4) */
+    int   kernel;     /* WaveNet.Kernel_Size (5) */
+    int   split;      /* Num_Split (4) */
+    int   spk_dim;    /* 0 (Vanilla) or Speaker_Embedding.Embedding_Size (SE-LUT) */
+    float dropout;    /* WaveNet.Dropout_Rate, applied only when seed != 0 */
+} glow_flow_config;
+
+typedef struct {
+    glow_flow_config cfg;
+    int       precision;     /* GLOW_F32: fp32 storage + CUDA-core fp32 math (parity mode)
+                                GLOW_BF16: bf16 activations/weights, tcgen05, fp32 accumulate */
+    int       batch, t_max;  /* mel tensors are [batch, 80, t_max] */
+    int       rows_pad;
+    int       training;      /* 1: keep every block's activations for glow_flow_backward */
+    uint64_t  seed;          /* dropout stream of this step; 0 = no dropout (eval) */
+    const int32_t *row_utt, *row_t, *utt_off, *utt_len;
+    const float *wpack;      /* glow_flow_prepare output (glow_flow_wpack_floats floats) */
+    const void  *wpack_tc;   /* bf16 slab images (glow_flow_wpack_tc_elems), bf16 mode only */
+    const float *spk;        /* [batch, spk_dim] speaker embeddings or NULL */
+    float *ws_f32; void *ws_act;   /* saved activations, sizes from glow_flow_workspace_elems */
+    float *bw_f32; void *bw_act;   /* backward scratch (may be NULL for forward / reverse) */
+    glow_stream_t stream;
+} glow_flow_call;
+
+int    glow_flow_param_slots(const glow_flow_config *cfg);
+size_t glow_flow_wpack_floats(const glow_flow_config *cfg);
+size_t glow_flow_wpack_tc_elems(const glow_flow_config *cfg);
+/* out[0..3] = elements of ws_f32 (f32), ws_act, bw_f32 (f32), bw_act; the *_act
+ * buffers hold f32 (GLOW_F32) or bf16 (GLOW_BF16) elements. */
+int    glow_flow_workspace_elems(const glow_flow_config *cfg, int rows_pad, int batch,
+                                 int training, size_t out[4]);
+/* weight_norm (g*v/||v||), exp(logs), W^-1 and logdet(W) of every block -> wpack. Once per step. */
+int    glow_flow_prepare(const glow_flow_config *cfg, const float *params,
+                         const int64_t *offsets_host, int precision,
+                         float *wpack, void *wpack_tc, glow_stream_t stream);
+/* mel [batch,80,t_max] -> z [batch,80,t_max] (zeros beyond each length), logdet [batch]. */
+int    glow_flow_forward(const glow_flow_call *call, const float *mel, float *z, float *logdet);
+/* z -> mel, positions beyond each length set to `fill` (Modules.py:202 uses -4). */
+int    glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel, float fill);
+/* dz [batch,80,t_max], dlogdet [batch] -> dwpack (grads of the effective weights, same
+ * layout as wpack, overwritten), optional dmel [batch,80,t_max], dspk [batch,spk_dim]. */
+int    glow_flow_backward(const glow_flow_call *call, const float *dz, const float *dlogdet,
+                          float *dwpack, float *dmel, float *dspk);
+/* dwpack -> gradients of the reference parameters (through weight_norm, exp, logdet), += into grads. */
+int    glow_flow_param_grads(const glow_flow_config *cfg, const float *params,
+                             const int64_t *offsets_host, const float *wpack,
+                             const float *dwpack, const float *dlogdet,
+                             const int32_t *utt_len, int batch, float *grads,
+                             glow_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Relative-position multi-head self-attention core
+ * replaces: RPR_MHA.py:95-128 Calc_Attention and its helpers :131-165
+ *           (Get_Relative_Embedding, Relative_Position_to_Absolute_Position,
+ *           Absolute_Position_to_Relative_Position) and their autograd backward.
+ * The 1x1 Query/Key/Value/Projection convs (RPR_MHA.py:82-93) stay with the
+ * caller; q, k, v, out are [batch, heads*head_dim, t] as those convs produce
+ * and consume them (channel = head*head_dim + e).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    const float *q, *k, *v;     /* [batch, heads*head_dim, t] */
+    const float *wk, *wv;       /* weight_K / weight_V [2*window+1, head_dim], shared over heads */
+    const int32_t *lengths;     /* [batch] valid length: mask(i,j) = i<len && j<len ; or NULL */
+    const float *mask;          /* [batch,1,t,t] 0/1, used when lengths == NULL; both NULL: no mask */
+    int   batch, heads, t, head_dim, window;
+    float dropout;              /* on the probabilities, only when seed != 0 */
+    uint64_t seed;
+    glow_stream_t stream;
+} glow_attn_call;
+
+/* out [batch, heads*head_dim, t]; probs [batch,heads,t,t] = softmax before dropout (needed by
+ * backward; may be NULL for inference); align = after dropout, what the reference returns as
+ * `alignments` (may be NULL). */
+int glow_rpr_attention_forward(const glow_attn_call *call, float *out, float *probs, float *align);
+/* dq, dk, dv like q; dwk, dwv [2*window+1, head_dim] are overwritten; ds_scratch [batch,heads,t,t]. */
+int glow_rpr_attention_backward(const glow_attn_call *call, const float *dout, const float *probs,
+                                float *ds_scratch, float *dq, float *dk, float *dv,
+                                float *dwk, float *dwv);
+
+/* ------------------------------------------------------------------------ *
  * Hardware self-test of the tcgen05 / TMEM / bulk-copy layer (csrc/umma.cuh):
  * d[128,n] f32 = a[shift..shift+127, :k] (bf16 row-major [rows_a,k]) times
  * b^T, where b_packed is the [n,k] bf16 weight pre-arranged in the kernels'

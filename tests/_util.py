@@ -54,3 +54,74 @@ def load_mas_case(name):
 
 
 MAS_CASE_NAMES = ["small_ragged", "ties", "mid_ragged", "lj_shaped", "ties_big"]
+
+
+# --------------------------------------------------------------------------- #
+# model fixtures
+# --------------------------------------------------------------------------- #
+def synth_state_dict(ref_sd, seed):
+    """Deterministic, non-degenerate values for every entry of a reference-layout
+    state_dict (same keys/shapes as `ref_sd`), independent of any constructor's init:
+    End convs are non-zero (the coupling is not the identity), ActNorm has non-trivial
+    logs/bias, 4x4 mixes are well conditioned with det > 0."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    out = {}
+    for key in sorted(ref_sd.keys()):
+        shape = tuple(ref_sd[key].shape)
+        r = torch.randn(shape, generator=g)
+        if key.endswith("layers.1.weight"):                       # 4x4 invertible conv
+            w = torch.eye(shape[0]) + 0.25 * r
+            if torch.det(w) < 0:
+                w[:, 0] = -w[:, 0]
+            v = w
+        elif key.endswith("weight_g"):
+            v = 0.6 + 0.4 * torch.rand(shape, generator=g)
+        elif key.endswith("weight_v"):
+            fan_in = shape[1] * shape[2]
+            v = r / fan_in ** 0.5
+        elif key.endswith("layers.0.logs"):
+            v = 0.15 * r
+        elif key.endswith("layers.0.bias"):
+            v = 0.2 * r
+        elif "LayerNorm" in key and key.endswith("weight"):
+            v = 1.0 + 0.1 * r
+        elif key.endswith("End.weight"):
+            v = 0.4 * r / shape[1] ** 0.5
+        elif key.endswith("bias"):
+            v = 0.05 * r
+        elif key.endswith("weight_K") or key.endswith("weight_V"):
+            v = r * shape[-1] ** -0.5
+        elif key.endswith("Embedding.weight"):
+            v = r * shape[1] ** -0.5
+        elif key.endswith("LUT.weight"):
+            v = 2 * torch.rand(shape, generator=g) - 1
+        elif len(shape) == 3:                                      # plain conv weights
+            v = r / (shape[1] * shape[2]) ** 0.5
+        else:
+            v = 0.1 * r
+        out[key] = v.float().contiguous()
+    return out
+
+
+def synth_batch(seed, token_lengths, mel_lengths, n_tokens=35, n_speakers=109, mel_dim=80):
+    """Collater-shaped batch (Datasets.py:225-250): tokens padded with <E>=1, mels padded with -4."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    b = len(token_lengths)
+    tx, ty = max(token_lengths), max(mel_lengths)
+    tokens = torch.ones(b, tx, dtype=torch.long)
+    mels = torch.full((b, mel_dim, ty), -4.0)
+    for i, (tl, ml) in enumerate(zip(token_lengths, mel_lengths)):
+        tokens[i, :tl] = torch.randint(2, n_tokens, (tl,), generator=g)
+        tokens[i, 0], tokens[i, tl - 1] = 0, 1
+        mels[i, :, :ml] = torch.clamp(1.5 * torch.randn(mel_dim, ml, generator=g), -4, 4)
+    speakers = torch.randint(0, n_speakers, (b,), generator=g)
+    return (tokens, torch.tensor(token_lengths), mels, torch.tensor(mel_lengths), speakers)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (the tolerance metric used throughout: 1e-3 per north_star)."""
+    import torch
+    a, b = torch.as_tensor(a).detach().double(), torch.as_tensor(b).detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

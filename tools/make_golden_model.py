@@ -1,0 +1,163 @@
+"""tools/make_golden_model.py -- model fixtures made by RUNNING THE REFERENCE MODULES
+(Modules.py, RPR_MHA.py, Radam.py, Noam_Scheduler.py imported from a temp copy of
+/root/reference with a patched Hyper_Parameters.yaml) on seeded synthetic inputs.
+Weights are NOT stored: they are regenerated from a seed by tests/_util.synth_state_dict
+(torch CPU RNG, same image on the GPU box); only key/shape tables, outputs, a checksum of
+the regenerated weights, and gradient digests are committed.  Run via tools/make_golden.py."""
+import importlib
+import json
+import math
+import os
+import shutil
+import sys
+
+import numpy as np
+import torch
+
+from tests._util import GOLD, checksum, synth_batch, synth_state_dict
+from tools.make_golden import stage_reference
+
+WEIGHT_SEED = {"Vanilla": 1234, "SE": 4321}
+CASES = {
+    # name: (mode, token_lengths, mel_lengths, batch seed)
+    "vanilla_small": ("Vanilla", [23, 17, 9], [140, 96, 50], 21),
+    "se_small": ("SE", [19, 12], [110, 64], 22),
+}
+
+
+def _fresh_import(dst):
+    for name in ("Modules", "RPR_MHA", "monotonic_align", "monotonic_align.monotonic_align",
+                 "monotonic_align.monotonic_align.core", "Radam", "Noam_Scheduler", "Arg_Parser",
+                 "Gradient_Reversal_Layer", "Speaker_Embedding", "Speaker_Embedding.Modules"):
+        sys.modules.pop(name, None)
+    importlib.invalidate_caches()
+    return importlib.import_module("Modules")
+
+
+def digest(t, seed):
+    """(norm, <t, r>) with a seeded random r: a 2-number fingerprint of a big gradient."""
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randn(t.shape, generator=g)
+    return [float(t.double().norm()), float((t.double() * r.double()).sum())]
+
+
+def run_mode(mode):
+    tmp, dst = stage_reference(mode, True)
+    cwd = os.getcwd()
+    try:
+        os.chdir(dst)
+        sys.path.insert(0, dst)
+        M = _fresh_import(dst)
+        import Radam, Noam_Scheduler
+        torch.manual_seed(0)
+        model = M.GlowTTS()
+        ref_sd = model.state_dict()
+        keys = [[k, list(v.shape)] for k, v in ref_sd.items()]
+        json.dump(keys, open(os.path.join(GOLD, "state_dict_keys_%s.json" % mode.lower()), "w"), indent=0)
+        sd = synth_state_dict(ref_sd, WEIGHT_SEED[mode])
+        model.load_state_dict(sd, strict=True)
+        for flow in model.layer_Dict["Decoder"].layer_Dict["Flows"]:
+            flow.layers[0].initialized = True
+        sd_sha = checksum(torch.cat([sd[k].flatten() for k in sorted(sd)]).numpy())
+        for name, (m, tls, mls, bseed) in CASES.items():
+            if m != mode:
+                continue
+            tokens, tl, mels, ml, spk = synth_batch(bseed, tls, mls)
+            out = {"weights_sha": sd_sha}
+            model.eval()
+            # ---- decoder alone: forward, reverse, backward digests
+            dec = model.layer_Dict["Decoder"]
+            mmask = model.Mask_Generate(ml)
+            emb = model.layer_Dict["LUT"](spk).detach() if mode == "SE" else None
+            z, logdet, _ = dec(mels, mmask, emb, None, None)
+            out["dec_z"], out["dec_logdet"] = z.detach().numpy(), logdet.detach().numpy()
+            with torch.no_grad():
+                back, _, _ = dec(z.detach(), mmask, emb, None, None, reverse=True)
+            out["dec_reverse_of_z"] = back.numpy()
+            g = torch.Generator().manual_seed(99)
+            rz, rl = torch.randn(z.shape, generator=g), torch.randn(logdet.shape, generator=g)
+            model.zero_grad()
+            ((z * rz).sum() + (logdet * rl).sum()).backward()
+            dgs = {k: digest(p.grad, 7) for k, p in dec.named_parameters()}
+            out["dec_grad_keys"] = np.array(list(dgs.keys()))
+            out["dec_grad_digest"] = np.array(list(dgs.values()), np.float64)
+            blk0 = dec.layer_Dict["Flows"][0]
+            out["dec_grad_b0_logs"] = blk0.layers[0].logs.grad.numpy().copy()
+            out["dec_grad_b0_w"] = blk0.layers[1].weight.grad.numpy().copy()
+            out["dec_grad_b0_start_g"] = blk0.layers[2].layer_Dict["Start"].weight_g.grad.numpy().copy()
+            out["dec_grad_b11_end_w"] = dec.layer_Dict["Flows"][-1].layers[2].layer_Dict["End"].weight.grad.numpy().copy()
+            # ---- one attention block: forward + backward
+            att = model.layer_Dict["Encoder"].layer_Dict["Transformer"].layer_Dict["ANCRDCN_0"].layer_Dict["Attention"]
+            g = torch.Generator().manual_seed(5)
+            xa = torch.randn(len(tls), 192, max(tls), generator=g, requires_grad=True)
+            tmask = model.Mask_Generate(tl)
+            amask = (tmask * tmask.transpose(2, 1)).unsqueeze(1)
+            ao, al = att(queries=xa, masks=amask)
+            ra = torch.randn(ao.shape, generator=g)
+            model.zero_grad()
+            (ao * ra).sum().backward()
+            out["att_x"], out["att_out"], out["att_align"] = xa.detach().numpy(), ao.detach().numpy(), al.detach().numpy()
+            out["att_dx"] = xa.grad.numpy().copy()
+            out["att_dwk"], out["att_dwv"] = att.weight_K.grad.numpy().copy(), att.weight_V.grad.numpy().copy()
+            out["att_dqw"] = att.layer_Dict["Query"].weight.grad.numpy().copy()
+            # ---- encoder
+            with torch.no_grad():
+                mean, log_std, logw, _ = model.layer_Dict["Encoder"](tokens, model.Mask_Generate(tl), emb, None)
+            out["enc_mean"], out["enc_log_std"], out["enc_logw"] = mean.numpy(), log_std.numpy(), logw.numpy()
+            # ---- full forward (eval) + losses + gradient digests
+            model.zero_grad()
+            res = model(tokens=tokens, token_lengths=tl, mels=mels, mel_lengths=ml, speakers=spk,
+                        mels_for_ge2e=None, pitches=None)
+            zf, mm, mls_, ld, lw, lwt, attn = res[:7]
+            mle = M.MLE_Loss()(z=zf, mean=mm, std=mls_, log_dets=ld, lengths=ml)
+            mse = torch.nn.MSELoss()(lw, lwt)
+            (mle + mse).backward()
+            out["fw_z"], out["fw_mel_mean"], out["fw_mel_log_std"] = zf.detach().numpy(), mm.detach().numpy(), mls_.detach().numpy()
+            out["fw_logdet"], out["fw_logw"], out["fw_logw_target"] = ld.detach().numpy(), lw.detach().numpy(), lwt.detach().numpy()
+            out["fw_attn_pos"] = attn.argmax(1).numpy().astype(np.int16)
+            out["fw_losses"] = np.array([float(mle), float(mse)])
+            dgs = {k: digest(p.grad, 11) for k, p in model.named_parameters() if p.grad is not None}
+            out["fw_grad_keys"] = np.array(list(dgs.keys()))
+            out["fw_grad_digest"] = np.array(list(dgs.values()), np.float64)
+            # ---- inference (noise_scale 0 -> deterministic)
+            with torch.no_grad():
+                im, il, ia = model.inference(tokens=tokens, token_lengths=tl, mels_for_prosody=None,
+                                             mel_lengths_for_prosody=None, speakers=spk, mels_for_ge2e=None,
+                                             pitches=None, pitch_lengths=None, noise_scale=0.0,
+                                             length_scale=torch.tensor([1.0] * len(tls)))
+            out["inf_mels"], out["inf_lengths"] = im.numpy(), il.numpy()
+            # ---- 3 train steps, dropout disabled (Train.py:182-233 restated around the reference modules)
+            model.load_state_dict(sd, strict=True)
+            model.eval()          # dropout off; nothing else in these modules depends on train/eval
+            opt = Radam.RAdam(params=model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-6)
+            sch = Noam_Scheduler.Modified_Noam_Scheduler(optimizer=opt, base=4000)
+            losses = []
+            for step in range(3):
+                res = model(tokens=tokens, token_lengths=tl, mels=mels, mel_lengths=ml, speakers=spk,
+                            mels_for_ge2e=None, pitches=None)
+                mle = M.MLE_Loss()(z=res[0], mean=res[1], std=res[2], log_dets=res[3], lengths=ml)
+                mse = torch.nn.MSELoss()(res[4], res[5])
+                opt.zero_grad()
+                (mle + mse).backward()
+                gn = torch.nn.utils.clip_grad_norm_(parameters=model.parameters(), max_norm=5.0)
+                opt.step(); sch.step()
+                losses.append([float(mle), float(mse), float(gn)])
+            out["train_losses"] = np.array(losses)
+            flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+            out["train_param_digest"] = np.array(digest(flat, 3))
+            np.savez_compressed(os.path.join(GOLD, "model_%s.npz" % name), **out)
+            print("model", name, "mle/mse", out["fw_losses"], "train", losses)
+            model.load_state_dict(sd, strict=True)
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(dst)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    for mode in ("Vanilla", "SE"):
+        run_mode(mode)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,7 +143,7 @@ class FlowDecoderFn(torch.autograd.Function):
     def forward(ctx, owner, rm, mel, spk, seed, *params):
         plan, device = owner.plan, mel.device
         tag, act_dtype = precision_tag(owner.precision)
-        training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        training = any(ctx.needs_input_grad)
         flat, offs = owner.flat_params()
         mel = mel.contiguous().float()
         spk_c = spk.contiguous().float() if spk is not None else None
@@ -161,7 +161,6 @@ class FlowDecoderFn(torch.autograd.Function):
         ctx.has_spk = spk is not None
         ctx.training = training
         ctx.n_params = len(params)
-        ctx.mark_non_differentiable()
         return z, logdet
 
     @staticmethod

@@ -31,9 +31,7 @@ class _AttnCoreFn(torch.autograd.Function):
         call.mask = mask_c.data_ptr() if mask_c is not None else None
         call.batch, call.heads, call.t, call.head_dim, call.window = b, heads, t, d, window
         call.dropout, call.seed = float(dropout), int(seed)
-        needs_grad = torch.is_grad_enabled() and any(
-            x.requires_grad for x in (q, k, v, wk, wv) if torch.is_tensor(x))
-        needs_grad = needs_grad or any(ctx.needs_input_grad[:5])
+        needs_grad = any(ctx.needs_input_grad[:5])
         out = torch.empty_like(q)
         probs = torch.empty((b, heads, t, t), dtype=torch.float32, device=dev) if needs_grad else None
         align = None

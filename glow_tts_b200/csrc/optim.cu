@@ -1,0 +1,97 @@
+// optim.cu -- one-launch optimizer step over the flat parameter / gradient buffers.
+//
+// Replaces the per-parameter Python loop of Radam.py:25-90 (fp32 temp copies, ~10 tiny
+// kernels per tensor x 515 tensors) and torch.nn.utils.clip_grad_norm_ (Train.py:227-231):
+//   glow_sqnorm      : sum g^2 over the flat gradient buffer (one float, atomics)
+//   glow_radam_step  : clip (coef = min(1, max_norm / (||g|| + 1e-6))) + RAdam update
+// The rectification scalars (N_sma, step_size) and the Noam learning rate are host
+// scalars, exactly as Radam.py:57-76 / Noam_Scheduler.py:17-29 compute them.
+#include "common.cuh"
+
+namespace glow {
+
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(const float *__restrict__ g, size_t n, float *__restrict__ out)
+{
+    __shared__ float s[8];
+    float acc = 0.f;
+    const size_t n4 = n >> 2;
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const float4 v = g4[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += 256) acc += g[i] * g[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s[i];
+        atomicAdd(out, t);
+    }
+}
+
+struct RadamArgs {
+    float lr, beta1, beta2, eps, weight_decay, step_size, max_norm, grad_scale;
+    int rectified;       // N_sma >= 5
+};
+
+__global__ void __launch_bounds__(256)
+radam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, size_t n,
+             RadamArgs a, const float *__restrict__ sqnorm, float *__restrict__ norm_out)
+{
+    float coef = a.grad_scale;
+    if (sqnorm != nullptr) {
+        const float total = sqrtf(*sqnorm) * a.grad_scale;
+        if (norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total;
+        if (a.max_norm > 0.f) coef *= fminf(1.f, a.max_norm / (total + 1e-6f));     // clip_grad_norm_
+    }
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float gi = g[i] * coef;
+        float pi = p[i];
+        const float vi = v[i] * a.beta2 + (1.f - a.beta2) * gi * gi;          // Radam.py:56
+        const float mi = m[i] * a.beta1 + (1.f - a.beta1) * gi;               // Radam.py:57
+        if (a.weight_decay != 0.f) pi += -a.weight_decay * a.lr * pi;         // Radam.py:78-79
+        if (a.rectified) pi += -a.step_size * a.lr * mi / (sqrtf(vi) + a.eps);   // Radam.py:82-84
+        else pi += -a.step_size * a.lr * mi;                                   // Radam.py:85-86
+        g[i] = gi; m[i] = mi; v[i] = vi; p[i] = pi;
+    }
+}
+
+}  // namespace glow
+
+using namespace glow;
+
+extern "C" {
+
+int glow_sqnorm(const float *g, size_t n, float *out, glow_stream_t stream)
+{
+    GLOW_REQUIRE(g && out, GLOW_ERR_INVALID, "sqnorm: null pointer");
+    GLOW_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, GLOW_ERR_INVALID, "sqnorm: g must be 16 B aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    GLOW_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+    if (n == 0) return GLOW_OK;
+    const int grid = (int)((n / 4 + 255) / 256 < (size_t)(kNumSMs * 8) ? (n / 4 + 255) / 256 + 1 : kNumSMs * 8);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(g, n, out);
+    GLOW_CHECK_LAUNCH("sqnorm_kernel");
+    return GLOW_OK;
+}
+
+int glow_radam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float step_size, int rectified, float max_norm,
+                    float grad_scale, const float *sqnorm, float *norm_out, glow_stream_t stream)
+{
+    GLOW_REQUIRE(params && grads && exp_avg && exp_avg_sq, GLOW_ERR_INVALID, "radam_step: null pointer");
+    if (n == 0) return GLOW_OK;
+    RadamArgs a{lr, beta1, beta2, eps, weight_decay, step_size, max_norm, grad_scale, rectified};
+    const size_t want = (n + 255) / 256;
+    const int grid = (int)(want < (size_t)(kNumSMs * 8) ? want : (size_t)(kNumSMs * 8));
+    radam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, a, sqnorm, norm_out);
+    GLOW_CHECK_LAUNCH("radam_kernel");
+    return GLOW_OK;
+}
+
+}  // extern "C"

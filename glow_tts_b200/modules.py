@@ -465,6 +465,7 @@ class Encoder(torch.nn.Module):
         h = _hp()
         e = h.Encoder
         self.channels, self.mel_dim = e.Channels, h.Sound.Mel_Dim
+        self.precision = getattr(h, "Precision", "bf16")
         self.layer_Dict = torch.nn.ModuleDict()
         self.layer_Dict["Embedding"] = torch.nn.Embedding(e.Embedding_Tokens, e.Channels)
         torch.nn.init.normal_(self.layer_Dict["Embedding"].weight, mean=0.0, std=e.Channels ** -0.5)
@@ -475,6 +476,11 @@ class Encoder(torch.nn.Module):
 
     def forward(self, x, mask, speakers=None, prosodies=None, lengths=None):
         _lib.require_cuda(mask, "Encoder mask")
+        # fp32 mode is the parity mode: keep cuDNN from silently using TF32 for the convs
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "fp32"):
+            return self._forward(x, mask, speakers, lengths)
+
+    def _forward(self, x, mask, speakers, lengths):
         d = self.layer_Dict
         y = d["Embedding"](x).transpose(2, 1) * math.sqrt(self.channels)
         y = d["Prenet"](y, mask)

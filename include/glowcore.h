@@ -198,6 +198,23 @@ int glow_rpr_attention_backward(const glow_attn_call *call, const float *dout, c
                                 float *dwk, float *dwv);
 
 /* ------------------------------------------------------------------------ *
+ * Optimizer step over the flat parameter / gradient buffers
+ * replaces: torch.nn.utils.clip_grad_norm_(max_norm) at Train.py:227-231 and
+ *           RAdam.step (Radam.py:25-90) -- the rectification scalars N_sma /
+ *           step_size (Radam.py:61-76) and the Noam learning rate
+ *           (Noam_Scheduler.py:17-29) stay host scalars passed in.
+ * ------------------------------------------------------------------------ */
+/* out[0] = sum g[i]^2 (out is zeroed first). g must be 16-byte aligned. */
+int glow_sqnorm(const float *g, size_t n, float *out, glow_stream_t stream);
+/* g <- g * grad_scale * min(1, max_norm / (grad_scale*sqrt(*sqnorm) + 1e-6))  (sqnorm NULL: no clip)
+ * then the RAdam update of Radam.py:56-86 with `rectified` = (N_sma >= 5).
+ * norm_out (nullable) receives the pre-clip gradient norm (what clip_grad_norm_ returns). */
+int glow_radam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float step_size, int rectified, float max_norm, float grad_scale,
+                    const float *sqnorm, float *norm_out, glow_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * Hardware self-test of the tcgen05 / TMEM / bulk-copy layer (csrc/umma.cuh):
  * d[128,n] f32 = a[shift..shift+127, :k] (bf16 row-major [rows_a,k]) times
  * b^T, where b_packed is the [n,k] bf16 weight pre-arranged in the kernels'

@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- mel-frames/sec of one full Glow-TTS train step on LJSpeech-shaped synthetic
+batches (BASELINE.json metric, config[1]: Vanilla, batch 32 per GPU, <= 1000 mel frames, bf16
+flow kernels), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference] [--workload train|mas|decoder]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); every rank runs the same code, rank 0
+prints ONE JSON line.  A "step" is forward + MLE/MSE losses + backward + ONE all-reduce of the
+flat gradient buffer + clip + RAdam + Noam (Train.py:182-233 of the reference) on one batch.
+
+* value  : real (unpadded) mel frames of all ranks / step time, inputs resident in HBM.
+* e2e    : same step through the public API with the batch in pinned HOST memory: H2D of the
+           batch and a D2H read of the loss are inside the timed region, every step.
+* roofline: the dominant kernel family (the coupling net's k=5 gated-conv GEMM, "in_gate"),
+           timed per launch with CUDA events by the library's own hook (glow_prof_*) during
+           extra steps run right after the timed region.
+* cpu_baseline / --impl reference: the CPU restatement of the reference's train step
+           (oracle/glow_oracle.py, torch-CPU fp32 + the reference's Cython MAS from oracle/_ref)
+           on all host threads, on a bounded sample of the same batch.  /root/reference is never
+           read here.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "mel_frames_per_sec_train_step"
+UNIT = "mel-frames/s"
+
+
+# ----------------------------------------------------------------------------- helpers
+def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the profiling guide's fallback."""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            flat = {}
+
+            def walk(x):
+                if isinstance(x, dict):
+                    for k, v in x.items():
+                        if isinstance(v, (int, float)):
+                            flat.setdefault(k, float(v))
+                        else:
+                            walk(v)
+            walk(d)
+            for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained"):
+                if k in flat:
+                    out[k] = flat[k]
+            out["source"] = "measured"
+        except Exception:
+            pass
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w": round(sum(power) / len(power), 1),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_cpu_model(mode, precision, seed=0):
+    """Random-init model of the reference architecture (there is no network for checkpoints).
+    End convs are zero-init in the reference (Modules.py:773-778), which makes every coupling the
+    identity at step 0; they get N(0, 0.01) here so the arithmetic is generic."""
+    import torch
+    from glow_tts_b200 import modules
+    from glow_tts_b200.hparams import load_hparams
+    hp = load_hparams(Mode=mode, Precision=precision)
+    modules.set_hparams(hp)
+    torch.manual_seed(seed)
+    model = modules.GlowTTS()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for blk in model.layer_Dict["Decoder"].layer_Dict["Flows"]:
+            end = blk.layers[2].layer_Dict["End"]
+            end.weight.copy_(0.01 * torch.randn(end.weight.shape, generator=g))
+    return model, hp
+
+
+def workload_batch(kind, batch, seed):
+    from glow_tts_b200.synth import make_batch
+    return make_batch(kind=kind, batch=batch, seed=seed)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_train_steps(model_sd, mode, batch, take, steps, warmup, threads=None):
+    """The oracle's train step (Train.py:182-233 restated) on the first `take` utterances of
+    `batch`, torch-CPU fp32, Cython MAS from oracle/_ref when it is there.  Returns
+    (frames_per_step, seconds_per_step list, cores, kind)."""
+    import torch
+    from oracle import glow_oracle as G
+    from oracle import mas as omas
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = G.OracleHP(mode=mode)
+    sd = G.state_dict_to_leaves(model_sd)
+    opt = G.RAdamOracle([v for v in sd.values() if v.requires_grad])
+    tokens, tl, mels, ml, spk = batch
+    tl, ml = tl[:take], ml[:take]
+    sub = (tokens[:take, :int(tl.max())].contiguous(), tl, mels[:take, :, :int(ml.max())].contiguous(), ml, spk[:take])
+    core = "ref" if omas.ref_core() is not None else "port"
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        G.train_step(sd, hp, opt, sub, training=True, mas_core=core)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return int(ml.sum()), times, cores, core
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    model, hp = build_cpu_model("Vanilla", "bf16")
+    batch = workload_batch("lj", args.batch, 0)
+    take = args.ref_sample
+    # size the sample so that the whole run ends within a few minutes
+    frames, t_probe, cores, core = cpu_train_steps(model.state_dict(), "Vanilla", batch, take, 1, 0)
+    budget = 200.0
+    while take > 1 and t_probe[0] * (args.steps + args.warmup) > budget:
+        take = max(1, take // 2)
+        frames, t_probe, cores, core = cpu_train_steps(model.state_dict(), "Vanilla", batch, take, 1, 0)
+    frames, times, cores, core = cpu_train_steps(model.state_dict(), "Vanilla", batch, take, args.steps, args.warmup)
+    sec = sum(times) / len(times)
+    value = frames / sec
+    sample = ("first %d of the %d utterances of the config batch (%d real mel frames) per step; oracle/glow_oracle.py "
+              "train step (torch-CPU fp32, %d threads) + %s MAS" %
+              (take, args.batch, frames, cores, "reference Cython (oracle/_ref)" if core == "ref" else "C port"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": own_config(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def own_config(args, extra):
+    cfg = {"workload": "configs[1]: Vanilla single-speaker, LJSpeech-shaped batch=%d per GPU, <=1000 mel frames, "
+                       "full train step (fwd+loss+bwd+allreduce+clip+RAdam)" % args.batch,
+           "mode": "Vanilla", "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+           "precision": args.precision, "parallelism": "dp%d" % args.gpus}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from glow_tts_b200 import _lib
+    from glow_tts_b200.train import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    model, hp = build_cpu_model("Vanilla", args.precision)
+    cpu_sd = {k: v.detach().clone() for k, v in model.state_dict().items()} if (rank == 0 and world == 1) else None
+    model = model.to(dev)
+    model.train()
+    step = TrainStep(model, hp, dev)
+
+    host = workload_batch("lj", args.batch, rank)          # every rank its own utterances (weak scaling)
+    tokens, tl, mels, ml, spk = host
+    pinned = (tokens.pin_memory(), tl, mels.pin_memory(), ml, spk.pin_memory())
+    real = int(ml.sum())
+    padded = int(mels.shape[0] * mels.shape[2])
+    counts = torch.tensor([float(real), float(tokens.numel()), float(padded)], device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    g_frames, g_pos, g_padded = (int(v) for v in counts.tolist())
+    dev_batch = step.to_device(pinned)
+
+    def one_step(b):
+        return step.run(b, global_frames=g_frames, global_positions=g_pos)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.profile_mode:
+        for _ in range(args.warmup):
+            one_step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("timed")
+        for _ in range(args.steps):
+            one_step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return 0
+
+    # warm-up (also runs the one-time ActNorm data-dependent init)
+    for _ in range(max(args.warmup, 3)):
+        one_step(dev_batch)
+    barrier()
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_step(dev_batch)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms)
+
+    # end to end through the public API: pinned host batch -> device -> step -> loss back on the host
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step(step.to_device(pinned))
+        loss_host = float(loss)                         # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2)
+    clocks = sampler.stop() if sampler else None
+    h2d = sum(t.numel() * t.element_size() for t in (pinned[0], pinned[2], pinned[4]))
+
+    # per-kernel-family device time (library hook), two more steps of the same workload
+    _lib.prof_enable(True)
+    for _ in range(2):
+        one_step(dev_batch)
+    torch.cuda.synchronize()
+    _lib.prof_enable(False)
+    prof = _lib.prof_report()
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    rows_real = sum(int(n) // 2 for n in ml.tolist())
+    fam = "in_gate"
+    roof = None
+    if fam in prof and prof[fam][0] > 0:
+        n, tot = prof[fam]
+        avg_ms = tot / n
+        flops = 2.0 * rows_real * 960 * 384                       # algorithmic: real squeezed frames x K x N
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(fam)
+        roof = {"bound": "tensor", "kernel": fam, "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "launches_timed": n,
+                "avg_launch_ms": avg_ms, "flops_per_launch": flops}
+    kernels = {k: {"launches_per_step": v[0] / 2.0, "ms_per_step": v[1] / 2.0} for k, v in sorted(prof.items())}
+    dec_ms = sum(v["ms_per_step"] for k, v in kernels.items() if not k.startswith(("rpr_", "mas")))
+    # the north_star's "fraction of the decoder's HBM roofline": algorithmic 4800 B x s per mel frame
+    # (s = 2 B bf16 / 4 B fp32) over the decoder GEMM time of one step
+    s_bytes = 2 if args.precision == "bf16" else 4
+    hbm = None
+    if dec_ms > 0:
+        gbs = real * 4800.0 * s_bytes / (dec_ms * 1e-3) / 1e9
+        hbm = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+               "note": "decoder GEMM kernels of one train step; compute is the binding roof (SURVEY 8d)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        frames, times, cores, core = cpu_train_steps(cpu_sd, "Vanilla", host, args.cpu_sample, 2, 1)
+        sec = sum(times) / len(times)
+        cpu = {"value": frames / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d of the %d utterances (%d real mel frames), 1 warm-up + 2 timed steps, "
+                         "oracle/glow_oracle.py (torch-CPU fp32) + %s MAS" %
+                         (args.cpu_sample, args.batch, frames,
+                          "reference Cython (oracle/_ref)" if core == "ref" else "C port")}
+
+    line = {
+        "metric": METRIC, "value": g_frames / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": own_config(args, {"real_mel_frames": g_frames, "padded_mel_frames": g_padded,
+                                    "l2": "no explicit flush: one step streams > 2 GB of saved activations "
+                                          "and 0.46 GB of parameter/optimizer state, >> 126 MB L2"}),
+        "padded_frames_per_sec": g_padded / (ms_per_step * 1e-3),
+        "e2e": {"value": g_frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "loss": loss_host},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / float(args.steps),
+        "clocks": clocks, "roofline": roof, "roofline_hbm_decoder": hbm, "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "mas", "decoder"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=8, help="utterances per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: exactly --warmup warm-up steps, then --steps steps, nothing else")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload != "train":
+        from tools import bench_extra
+        return bench_extra.run(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

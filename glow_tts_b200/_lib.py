@@ -46,6 +46,8 @@ SIGNATURES = {
     "glow_abi_version": (_I, []),
     "glow_last_error": (_c.c_char_p, []),
     "glow_launch_count": (_U64, []),
+    "glow_prof_enable": (_I, [_I]),
+    "glow_prof_report": (_I, [_c.c_char_p, _Z]),
     "glow_mas_workspace_bytes": (_Z, [_I, _I, _I]),
     "glow_mas_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _P, _Z, _P]),
     "glow_mas_forward_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _I]),
@@ -113,6 +115,21 @@ def require_cuda(t, name):
 
 def launch_count():
     return int(lib().glow_launch_count())
+
+
+def prof_enable(on):
+    check(lib().glow_prof_enable(int(bool(on))), "glow_prof_enable")
+
+
+def prof_report():
+    """{kernel family: (launches, total_ms)} since profiling was enabled; clears the log."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().glow_prof_report(buf, len(buf)), "glow_prof_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def header_symbols():

@@ -386,6 +386,7 @@ int glow_rpr_attention_forward(const glow_attn_call *c, float *out, float *probs
     const size_t smem = attn_smem_bytes(c->t);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c->t + kAQ - 1) / kAQ, c->heads, c->batch);
+    ProfScope prof("rpr_attn_fwd", (cudaStream_t)c->stream);
     rpr_attn_fwd_kernel<<<grid, kAThreads, smem, (cudaStream_t)c->stream>>>(a);
     GLOW_CHECK_LAUNCH("rpr_attn_fwd_kernel");
     return GLOW_OK;
@@ -408,6 +409,7 @@ int glow_rpr_attention_backward(const glow_attn_call *c, const float *dout, cons
     const size_t smem = attn_smem_bytes(c->t);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c->t + kAQ - 1) / kAQ, c->heads, c->batch);
+    ProfScope prof("rpr_attn_bwd", st);
     rpr_attn_bwd_q_kernel<<<grid, kAThreads, smem, st>>>(a);
     GLOW_CHECK_LAUNCH("rpr_attn_bwd_q_kernel");
     rpr_attn_bwd_kv_kernel<<<grid, kAThreads, 0, st>>>(a);

@@ -42,6 +42,17 @@ void  count_launch(int n = 1);
         if (!(cond)) return ::glow::fail(code, __VA_ARGS__);                         \
     } while (0)
 
+// Optional per-launch device timing (glow_prof_enable / glow_prof_report): when enabled,
+// a ProfScope around a launch records a CUDA event before and after it on the launch
+// stream; the report sums the elapsed time per name.  Off by default (zero overhead).
+struct ProfScope {
+    const char *name;
+    cudaStream_t st;
+    void *slot;
+    ProfScope(const char *name, cudaStream_t st);
+    ~ProfScope();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -85,6 +85,7 @@ int gemm_simt(const ALoad &aload, const float *W, int Ktot, int N, int rows_pad,
               const char *name)
 {
     dim3 grid(rows_pad / 64, (N + 63) / 64);
+    ProfScope prof(name, st);
     simt_gemm_kernel<ALoad, Epi><<<grid, 256, 0, st>>>(aload, W, Ktot, N, epi);
     GLOW_CHECK_LAUNCH(name);
     return GLOW_OK;

@@ -191,6 +191,7 @@ static int launch_mas(const float *value, const float *mask, const int32_t *t_x,
     GLOW_REQUIRE(smem <= 227 * 1024, GLOW_ERR_UNSUPPORTED,
                  "mas: t_y_max=%d needs %zu B of shared memory (> 227 KB)", Ty, smem);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(mas_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof("mas", st);
     mas_kernel<E><<<B, kMasThreads, smem, st>>>(value, mask, t_x, t_y, Tx, Ty, path, one_bits, neg);
     GLOW_CHECK_LAUNCH("mas_kernel");
     return GLOW_OK;

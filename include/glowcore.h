@@ -43,6 +43,12 @@ const char *glow_last_error(void);
 /* Number of kernels this library has launched in the calling process (the
  * bench's "gpu_launches" claim is read from here, not estimated). */
 uint64_t    glow_launch_count(void);
+/* Per-launch device timing for bench.py's roofline line (no reference counterpart).
+ * While enabled, the library brackets each of its GEMM / MAS / attention launches with
+ * CUDA events on the launch stream.  glow_prof_report synchronises on those events and
+ * writes one "name launches total_ms\n" line per kernel family into buf, then clears. */
+int         glow_prof_enable(int on);
+int         glow_prof_report(char *buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------ *
  * Monotonic alignment search

@@ -404,7 +404,7 @@ def train_step(sd, hp, opt, batch, training=True, mas_core="port", clip=5.0):
     total.backward()
     torch.nn.utils.clip_grad_norm_([p for p in opt.params if p.grad is not None], clip)   # Train.py:227-231
     opt.step()
-    return float(total), float(mle), float(length)
+    return float(total.detach()), float(mle.detach()), float(length.detach())
 
 
 def state_dict_to_leaves(sd):

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libglowcore.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "glowcore.h")
 
-GLOW_F32, GLOW_I32, GLOW_BF16 = 0, 1, 2
+GLOW_F32, GLOW_I32, GLOW_BF16, GLOW_BF16_SIMT = 0, 1, 2, 3
 
 _c = ctypes
 _P, _I, _F, _Z, _U64, _U32 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint64, _c.c_uint32

@@ -17,6 +17,96 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat16
 __device__ __forceinline__ void stf(float *p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16(v); }
 
+// ---- row-segment loads / stores: N consecutive elements starting at an address aligned to
+// N elements (the epilogues' column offsets are multiples of their NV), widest vector that fits.
+template <int N> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[N])
+{
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 t = reinterpret_cast<const float4 *>(p)[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float2 t = reinterpret_cast<const float2 *>(p)[i];
+            v[2 * i] = t.x; v[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = p[i];
+    }
+}
+template <int N> __device__ __forceinline__ void st_vec(float *p, const float (&v)[N])
+{
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i)
+            reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) reinterpret_cast<float2 *>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = v[i];
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float &lo, float &hi)
+{
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w));
+    lo = f.x; hi = f.y;
+}
+template <int N> __device__ __forceinline__ void ld_vec(const __nv_bfloat16 *p, float (&v)[N])
+{
+    if constexpr (N % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i) {
+            const uint4 t = reinterpret_cast<const uint4 *>(p)[i];
+            unpack_bf16x2(t.x, v[8 * i], v[8 * i + 1]); unpack_bf16x2(t.y, v[8 * i + 2], v[8 * i + 3]);
+            unpack_bf16x2(t.z, v[8 * i + 4], v[8 * i + 5]); unpack_bf16x2(t.w, v[8 * i + 6], v[8 * i + 7]);
+        }
+    } else if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const uint2 t = reinterpret_cast<const uint2 *>(p)[i];
+            unpack_bf16x2(t.x, v[4 * i], v[4 * i + 1]); unpack_bf16x2(t.y, v[4 * i + 2], v[4 * i + 3]);
+        }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) unpack_bf16x2(reinterpret_cast<const uint32_t *>(p)[i], v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __bfloat162float(p[i]);
+    }
+}
+template <int N> __device__ __forceinline__ void st_vec(__nv_bfloat16 *p, const float (&v)[N])
+{
+    if constexpr (N % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i)
+            reinterpret_cast<uint4 *>(p)[i] =
+                make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    } else if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i)
+            reinterpret_cast<uint2 *>(p)[i] =
+                make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) reinterpret_cast<uint32_t *>(p)[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = __float2bfloat16(v[i]);
+    }
+}
+
 template <bool FAST> __device__ __forceinline__ float tanh_t(float x)
 {
     if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -61,8 +151,11 @@ struct EpiStart {
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         const bool m = row_utt[row] >= 0;
+        float b[NV], out[NV];
+        ld_vec<NV>(bias + n0, b);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) stf(H + (size_t)row * kH + n0 + j, m ? v[j] + bias[n0 + j] : 0.f);
+        for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + b[j] : 0.f;
+        st_vec<NV>(H + (size_t)row * kH + n0, out);
     }
 };
 
@@ -74,21 +167,25 @@ struct EpiGate {
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         const int b = row_utt[row];
+        float bs[NV], ts[NV], acts[NV / 2];
+        ld_vec<NV>(bias + n0, bs);
 #pragma unroll
         for (int j = 0; j < NV / 2; ++j) {
             const int n = n0 + 2 * j;
             float t = 0.f, s = 0.f;
             if (b >= 0) {
-                float pt = drop.apply(v[2 * j] + bias[n], row, n);
-                float ps = drop.apply(v[2 * j + 1] + bias[n + 1], row, n + 1);
+                float pt = drop.apply(v[2 * j] + bs[2 * j], row, n);
+                float ps = drop.apply(v[2 * j + 1] + bs[2 * j + 1], row, n + 1);
                 if (spkb != nullptr) { pt += spkb[(size_t)b * kG + n]; ps += spkb[(size_t)b * kG + n + 1]; }
                 t = tanh_t<FAST>(pt);
                 s = sigmoid_t<FAST>(ps);
             }
-            stf(TS + (size_t)row * kG + n, t);
-            stf(TS + (size_t)row * kG + n + 1, s);
-            stf(ACTS + (size_t)row * kH + (n >> 1), t * s);
+            ts[2 * j] = t;
+            ts[2 * j + 1] = s;
+            acts[j] = t * s;
         }
+        st_vec<NV>(TS + (size_t)row * kG + n0, ts);
+        st_vec<NV / 2>(ACTS + (size_t)row * kH + (n0 >> 1), acts);
     }
 };
 
@@ -99,21 +196,26 @@ struct EpiResSkip {
     int first, last;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
+        // n0 is a multiple of NV and NV divides kH, so the NV columns lie on one side of the res | skip split
         const bool m = row_utt[row] >= 0;
+        float b[NV], out[NV], old[NV];
+        ld_vec<NV>(bias + n0, b);
+        if (last) {
+            if (!first) ld_vec<NV>(SKIP + (size_t)row * kH + n0, old);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int n = n0 + j;
-            const float val = v[j] + bias[n];
-            if (last) {
-                const float acc = val + (first ? 0.f : SKIP[(size_t)row * kH + n]);
-                stf(OUT + (size_t)row * kH + n, m ? acc : 0.f);                        // :881,:883
-            } else if (n < kH) {
-                const float h = ldf(Hin + (size_t)row * kH + n);
-                stf(Hout + (size_t)row * kH + n, m ? h + val : 0.f);                   // :878
-            } else {
-                float *sk = SKIP + (size_t)row * kH + (n - kH);
-                *sk = first ? val : *sk + val;                                          // :879
-            }
+            for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + b[j] + (first ? 0.f : old[j]) : 0.f;   // :881,:883
+            st_vec<NV>(OUT + (size_t)row * kH + n0, out);
+        } else if (n0 < kH) {
+            ld_vec<NV>(Hin + (size_t)row * kH + n0, old);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) out[j] = m ? old[j] + (v[j] + b[j]) : 0.f;                  // :878
+            st_vec<NV>(Hout + (size_t)row * kH + n0, out);
+        } else {
+            float *sk = SKIP + (size_t)row * kH + (n0 - kH);
+            if (!first) ld_vec<NV>(sk, old);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) out[j] = first ? v[j] + b[j] : old[j] + (v[j] + b[j]);      // :879
+            st_vec<NV>(sk, out);
         }
     }
 };
@@ -141,20 +243,19 @@ struct EpiEnd {
     {
         const bool m = row_utt[row] >= 0;
         const int c0 = n0 >> 1;
-        float za[NV / 2], zb[NV / 2];
+        float za[NV / 2], zb[NV / 2], bs[NV], outs[NV], oa[NV / 2], ob[NV / 2];
         float ld = 0.f;
+        ld_vec<NV>(bias + n0, bs);
+        ld_vec<NV / 2>(Y + (size_t)row * kC + c0, za);
+        ld_vec<NV / 2>(Y + (size_t)row * kC + kCh + c0, zb);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) outs[j] = v[j] + bs[j];
+        if (OUTS != nullptr) st_vec<NV>(OUTS + (size_t)row * kC + n0, outs);
 #pragma unroll
         for (int j = 0; j < NV / 2; ++j) {
-            const int c = c0 + j;
-            const float mean = v[2 * j] + bias[n0 + 2 * j];
-            const float logs = v[2 * j + 1] + bias[n0 + 2 * j + 1];
-            if (OUTS != nullptr) {
-                OUTS[(size_t)row * kC + n0 + 2 * j] = mean;
-                OUTS[(size_t)row * kC + n0 + 2 * j + 1] = logs;
-            }
-            const float xa = Y[(size_t)row * kC + c];
-            const float xb = Y[(size_t)row * kC + kCh + c];
-            za[j] = xa;
+            const float mean = outs[2 * j];
+            const float logs = outs[2 * j + 1];
+            const float xb = zb[j];
             if (!reverse) {
                 zb[j] = m ? mean + exp_t<FAST>(logs) * xb : 0.f;                        // :805
                 ld += m ? logs : 0.f;                                                    // :806
@@ -189,13 +290,13 @@ struct EpiEnd {
                     out[o] = m ? (u - mix_bias[ch]) / mix_scale[ch] : 0.f;               // :690
                 }
             }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int ch = group_channel(g, o);
-                Ynext[(size_t)row * kC + ch] = out[o];
-                if (YAnext != nullptr && o < 2) stf(YAnext + (size_t)row * kCh + ch, out[o]);
-            }
+            oa[2 * q] = out[0]; oa[2 * q + 1] = out[1];
+            ob[2 * q] = out[2]; ob[2 * q + 1] = out[3];
         }
+        // group g's channels are {2g, 2g+1} of each half: the NV/4 groups cover c0 .. c0+NV/2-1 of both halves
+        st_vec<NV / 2>(Ynext + (size_t)row * kC + c0, oa);
+        st_vec<NV / 2>(Ynext + (size_t)row * kC + kCh + c0, ob);
+        if (YAnext != nullptr) st_vec<NV / 2>(YAnext + (size_t)row * kCh + c0, oa);
     }
 };
 
@@ -207,8 +308,10 @@ struct EpiBwdEnd {
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         const bool m = row_utt[row] >= 0;
+        float out[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) stf(DOUT + (size_t)row * kH + n0 + j, m ? v[j] : 0.f);
+        for (int j = 0; j < NV; ++j) out[j] = m ? v[j] : 0.f;
+        st_vec<NV>(DOUT + (size_t)row * kH + n0, out);
     }
 };
 
@@ -220,19 +323,19 @@ struct EpiBwdGate {
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         const bool m = row_utt[row] >= 0;
+        float ts[2 * NV], dins[2 * NV];
+        ld_vec<2 * NV>(TS + (size_t)row * kG + 2 * n0, ts);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int c = n0 + j;
-            const float t = ldf(TS + (size_t)row * kG + 2 * c);
-            const float s = ldf(TS + (size_t)row * kG + 2 * c + 1);
-            const float dt = m ? v[j] * s * (1.f - t * t) : 0.f;
-            const float ds = m ? v[j] * t * s * (1.f - s) : 0.f;
-            stf(DINS + (size_t)row * kG + 2 * c, dt);
-            stf(DINS + (size_t)row * kG + 2 * c + 1, ds);
-            if (DPRE != DINS) {
-                stf(DPRE + (size_t)row * kG + 2 * c, drop.apply(dt, row, 2 * c));
-                stf(DPRE + (size_t)row * kG + 2 * c + 1, drop.apply(ds, row, 2 * c + 1));
-            }
+            const float t = ts[2 * j], s = ts[2 * j + 1];
+            dins[2 * j] = m ? v[j] * s * (1.f - t * t) : 0.f;
+            dins[2 * j + 1] = m ? v[j] * t * s * (1.f - s) : 0.f;
+        }
+        st_vec<2 * NV>(DINS + (size_t)row * kG + 2 * n0, dins);
+        if (DPRE != DINS) {
+#pragma unroll
+            for (int j = 0; j < 2 * NV; ++j) dins[j] = drop.apply(dins[j], row, 2 * n0 + j);
+            st_vec<2 * NV>(DPRE + (size_t)row * kG + 2 * n0, dins);
         }
     }
 };
@@ -244,12 +347,12 @@ struct EpiBwdIn {
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         const bool m = row_utt[row] >= 0;
+        const size_t o = (size_t)row * kH + n0;
+        float r[NV], out[NV];
+        if (DHnext != nullptr) ld_vec<NV>(DHnext + o, r);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const size_t o = (size_t)row * kH + n0 + j;
-            const float r = DHnext != nullptr ? ldf(DHnext + o) : 0.f;
-            stf(DH + o, m ? v[j] + r : 0.f);
-        }
+        for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + (DHnext != nullptr ? r[j] : 0.f) : 0.f;
+        st_vec<NV>(DH + o, out);
     }
 };
 
@@ -258,8 +361,11 @@ struct EpiBwdStart {
     float *DY;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
+        float old[NV];
+        ld_vec<NV>(DY + (size_t)row * kC + n0, old);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) DY[(size_t)row * kC + n0 + j] += v[j];
+        for (int j = 0; j < NV; ++j) old[j] += v[j];
+        st_vec<NV>(DY + (size_t)row * kC + n0, old);
     }
 };
 

@@ -32,8 +32,8 @@ static int check_call(const glow_flow_call *call, bool need_bwd)
     GLOW_REQUIRE(call != nullptr, GLOW_ERR_INVALID, "flow: null call");
     int rc = check_cfg(&call->cfg);
     if (rc) return rc;
-    GLOW_REQUIRE(call->precision == GLOW_F32 || call->precision == GLOW_BF16, GLOW_ERR_INVALID,
-                 "flow: precision must be GLOW_F32 or GLOW_BF16");
+    GLOW_REQUIRE(call->precision == GLOW_F32 || call->precision == GLOW_BF16 || call->precision == GLOW_BF16_SIMT,
+                 GLOW_ERR_INVALID, "flow: precision must be GLOW_F32, GLOW_BF16 or GLOW_BF16_SIMT");
     GLOW_REQUIRE(call->batch >= 1 && call->t_max >= 2, GLOW_ERR_INVALID, "flow: batch=%d t_max=%d", call->batch,
                  call->t_max);
     GLOW_REQUIRE(call->rows_pad > 0 && call->rows_pad % kRowTile == 0, GLOW_ERR_INVALID,
@@ -174,12 +174,12 @@ int glow_flow_prepare(const glow_flow_config *cfg, const float *params, const in
     int rc = check_cfg(cfg);
     if (rc) return rc;
     GLOW_REQUIRE(params && offsets_host && wpack, GLOW_ERR_INVALID, "flow_prepare: null pointer");
-    GLOW_REQUIRE(precision == GLOW_F32 || (precision == GLOW_BF16 && wpack_tc), GLOW_ERR_INVALID,
-                 "flow_prepare: bad precision / missing wpack_tc");
+    GLOW_REQUIRE(precision == GLOW_F32 || ((precision == GLOW_BF16 || precision == GLOW_BF16_SIMT) && wpack_tc),
+                 GLOW_ERR_INVALID, "flow_prepare: bad precision / missing wpack_tc");
     const FlowCfg fc = to_cfg(cfg);
     static thread_local WnJobs jobs;
     SmallJobs small{};
-    build_jobs(fc, params, offsets_host, nullptr, wpack, precision == GLOW_BF16 ? (__nv_bfloat16 *)wpack_tc : nullptr,
+    build_jobs(fc, params, offsets_host, nullptr, wpack, precision != GLOW_F32 ? (__nv_bfloat16 *)wpack_tc : nullptr,
                nullptr, &jobs, &small);
     const BlockPack bp = make_block_pack(cfg->spk_dim);
     rc = launch_block_small(small, wpack, bp.total, bp, (cudaStream_t)stream);
@@ -212,7 +212,7 @@ int glow_flow_forward(const glow_flow_call *call, const float *mel, float *z, fl
     if (rc) return rc;
     GLOW_REQUIRE(mel && z && logdet, GLOW_ERR_INVALID, "flow_forward: null pointer");
     if (call->precision == GLOW_F32) return flow_forward_f32(make_ctx<float>(call), mel, call->t_max, z, logdet);
-    return flow_forward_bf16(make_ctx<__nv_bfloat16>(call), mel, call->t_max, z, logdet);
+    return flow_forward_bf16(make_ctx<__nv_bfloat16>(call), mel, call->t_max, z, logdet, call->precision == GLOW_BF16);
 }
 
 int glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel, float fill)
@@ -221,7 +221,7 @@ int glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel, fl
     if (rc) return rc;
     GLOW_REQUIRE(mel && z, GLOW_ERR_INVALID, "flow_reverse: null pointer");
     if (call->precision == GLOW_F32) return flow_reverse_f32(make_ctx<float>(call), z, call->t_max, mel, fill);
-    return flow_reverse_bf16(make_ctx<__nv_bfloat16>(call), z, call->t_max, mel, fill);
+    return flow_reverse_bf16(make_ctx<__nv_bfloat16>(call), z, call->t_max, mel, fill, call->precision == GLOW_BF16);
 }
 
 int glow_flow_backward(const glow_flow_call *call, const float *dz, const float *dlogdet, float *dwpack, float *dmel,
@@ -236,7 +236,8 @@ int glow_flow_backward(const glow_flow_call *call, const float *dz, const float 
                                         (cudaStream_t)call->stream));
     if (call->precision == GLOW_F32)
         return flow_backward_f32(make_ctx<float>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk);
-    return flow_backward_bf16(make_ctx<__nv_bfloat16>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk);
+    return flow_backward_bf16(make_ctx<__nv_bfloat16>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk,
+                              call->precision == GLOW_BF16);
 }
 
 }  // extern "C"

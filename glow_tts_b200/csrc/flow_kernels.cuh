@@ -70,10 +70,11 @@ int flow_reverse_f32(const FlowCtx<float> &c, const float *z, int T, float *mel,
 int flow_backward_f32(const FlowCtx<float> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
                       float *dmel, float *dspk);
 // bf16 tcgen05 path (flow_tc.cu)
-int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet);
-int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill);
+// (tc = true) and the same bf16 storage on the CUDA-core GEMM (tc = false, cross-check only)
+int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet, bool tc);
+int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill, bool tc);
 int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
-                       float *dmel, float *dspk);
+                       float *dmel, float *dspk, bool tc);
 
 // cuBLAS weight-gradient GEMMs (flow_wgrad.cu), row-major:
 //   C[b][K][N] (ldc) = beta*C + A_b[rows,K]^T * D[rows,N],  A_b = A + b*strideA, C_b = C + b*strideC

@@ -1,24 +1,27 @@
-// flow_tc.cu -- bf16 instantiation of the flow decoder.
-// Step 1 (this file as it stands): bf16 activations on the shared orchestration with
-// the CUDA-core GEMM; the tcgen05 ops replace SimtOps one by one (TcOps below).
-#include "flow_run.cuh"
+// flow_tc.cu -- bf16 instantiations of the flow decoder: the tcgen05 path (GLOW_BF16) and, for
+// on-device cross-checks of it, the same bf16 storage on the CUDA-core GEMM (GLOW_BF16_SIMT).
+#include "flow_tc.cuh"
 
 namespace glow {
 
-using OpsBf16 = SimtOps<__nv_bfloat16, true>;
+using OpsTc = TcOps<true>;
+using OpsBf16Simt = SimtOps<__nv_bfloat16, true>;
 
-int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet)
+int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet, bool tc)
 {
-    return flow_forward_impl<__nv_bfloat16, true, OpsBf16>(c, mel, T, z, logdet);
+    if (tc) return flow_forward_impl<__nv_bfloat16, true, OpsTc>(c, mel, T, z, logdet);
+    return flow_forward_impl<__nv_bfloat16, true, OpsBf16Simt>(c, mel, T, z, logdet);
 }
-int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill)
+int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill, bool tc)
 {
-    return flow_reverse_impl<__nv_bfloat16, true, OpsBf16>(c, z, T, mel, fill);
+    if (tc) return flow_reverse_impl<__nv_bfloat16, true, OpsTc>(c, z, T, mel, fill);
+    return flow_reverse_impl<__nv_bfloat16, true, OpsBf16Simt>(c, z, T, mel, fill);
 }
 int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
-                       float *dmel, float *dspk)
+                       float *dmel, float *dspk, bool tc)
 {
-    return flow_backward_impl<__nv_bfloat16, true, OpsBf16>(c, dz, T, dlogdet, dwpack, dmel, dspk);
+    if (tc) return flow_backward_impl<__nv_bfloat16, true, OpsTc>(c, dz, T, dlogdet, dwpack, dmel, dspk);
+    return flow_backward_impl<__nv_bfloat16, true, OpsBf16Simt>(c, dz, T, dlogdet, dwpack, dmel, dspk);
 }
 
 }  // namespace glow

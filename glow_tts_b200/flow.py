@@ -61,7 +61,9 @@ def precision_tag(precision):
         return _lib.GLOW_F32, torch.float32
     if precision in ("bf16", torch.bfloat16):
         return _lib.GLOW_BF16, torch.bfloat16
-    raise ValueError("precision must be 'fp32' or 'bf16', got %r" % (precision,))
+    if precision == "bf16-simt":          # bf16 storage on the CUDA-core GEMM: device cross-check of the tcgen05 path
+        return _lib.GLOW_BF16_SIMT, torch.bfloat16
+    raise ValueError("precision must be 'fp32', 'bf16' or 'bf16-simt', got %r" % (precision,))
 
 
 class FlowPlan:
@@ -86,7 +88,7 @@ class FlowPlan:
         if key not in self._wpack:
             wp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
             wtc = (torch.empty(self.wpack_tc_elems, dtype=torch.bfloat16, device=device)
-                   if tag == _lib.GLOW_BF16 else None)
+                   if tag != _lib.GLOW_F32 else None)
             dwp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
             self._wpack[key] = (wp, wtc, dwp)
         return self._wpack[key]

@@ -37,6 +37,7 @@ typedef void *glow_stream_t;        /* cudaStream_t */
 #define GLOW_F32   0
 #define GLOW_I32   1
 #define GLOW_BF16  2
+#define GLOW_BF16_SIMT 3   /* flow precision only: bf16 storage on the CUDA-core GEMM (device cross-check of GLOW_BF16) */
 
 int         glow_abi_version(void);
 const char *glow_last_error(void);
@@ -134,7 +135,8 @@ typedef struct {
 typedef struct {
     glow_flow_config cfg;
     int       precision;     /* GLOW_F32: fp32 storage + CUDA-core fp32 math (parity mode)
-                                GLOW_BF16: bf16 activations/weights, tcgen05, fp32 accumulate */
+                                GLOW_BF16: bf16 activations/weights, tcgen05, fp32 accumulate
+                                GLOW_BF16_SIMT: same storage, CUDA-core GEMM (cross-check) */
     int       batch, t_max;  /* mel tensors are [batch, 80, t_max] */
     int       rows_pad;
     int       training;      /* 1: keep every block's activations for glow_flow_backward */

@@ -255,6 +255,35 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.trace:
+        # torch.profiler (CUPTI) over a few steps: where the step's device time and host time go
+        from torch.profiler import profile, ProfilerActivity
+        for _ in range(max(args.warmup, 3)):
+            one_step(dev_batch)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            one_step(dev_batch)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 5
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(args.steps):
+                one_step(dev_batch)
+            torch.cuda.synchronize()
+        ev = prof.key_averages()
+        from torch.autograd import DeviceType
+        rows = [(e.key, e.count, e.self_device_time_total / 1e3) for e in ev
+                if e.self_device_time_total > 0 and e.device_type == DeviceType.CUDA]
+        rows.sort(key=lambda r: -r[2])
+        tot = sum(r[2] for r in rows)
+        print("# wall %.3f ms/step (unprofiled); device-busy %.3f ms/step over %d steps" %
+              (wall * 1e3, tot / args.steps, args.steps))
+        print("| kernel | launches/step | ms/step | share |\n|---|---:|---:|---:|")
+        for k, n, ms in rows[:60]:
+            print("| `%s` | %.1f | %.3f | %.1f%% |" % (k[:90], n / args.steps, ms / args.steps, 100 * ms / tot))
+        print("| total | %.1f | %.3f | 100%% |" % (sum(r[1] for r in rows) / args.steps, tot / args.steps))
+        return 0
+
     if args.profile_mode:
         for _ in range(args.warmup):
             one_step(dev_batch)
@@ -385,6 +414,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=8, help="utterances per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--trace", action="store_true", help="torch.profiler kernel table of the step instead of the bench line")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: exactly --warmup warm-up steps, then --steps steps, nothing else")
     args = ap.parse_args()

@@ -123,23 +123,41 @@ template <bool FAST> __device__ __forceinline__ float exp_t(float x)
 }
 
 // ---- dropout on the gate pre-activation (Modules.py:862) -----------------------
-// Counter-based: keep(seed, element index) is recomputed identically in backward.
-__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, float p)
+// Counter-based: the keep decision of element (row, n) is a pure function of (seed, layer,
+// row, n), recomputed identically in backward.  One 32-bit hash (murmur3 finaliser) decides
+// a PAIR of adjacent packed columns with 16 bits each: keep iff bits >= thresh, thresh =
+// round(p * 65536); survivors are scaled by 65536 / (65536 - thresh), the exact inverse of the
+// keep probability.
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
 {
-    uint64_t x = seed ^ (idx * 0x9E3779B97F4A7C15ull);
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
-    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
-    x ^= x >> 33;
-    return (float)(uint32_t)(x >> 40) * (1.f / 16777216.f) >= p;
+    x ^= x >> 16; x *= 0x85ebca6bu;
+    x ^= x >> 13; x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
 }
 struct DropCfg {
     uint64_t seed;      // 0 -> disabled
     uint64_t base;      // (block * layers + layer) * rows_pad
-    float p, inv_keep;  // p, 1/(1-p)
-    __device__ __forceinline__ float apply(float v, int row, int n) const
+    float p, inv_keep;  // p, 1/(1-p) (inv_keep is re-derived from the 16-bit threshold on the device)
+    // keep bits of packed columns (n, n+1), n even: bit 0 -> column n, bit 1 -> column n+1
+    __device__ __forceinline__ uint32_t thresh() const { return (uint32_t)(p * 65536.f + 0.5f); }
+    __device__ __forceinline__ float scale() const { return 65536.f / (65536.f - (float)thresh()); }
+    __device__ __forceinline__ uint32_t keep2(int row, int n) const
     {
-        if (seed == 0) return v;
-        return drop_keep(seed, (base + (uint64_t)row) * kG + (uint64_t)n, p) ? v * inv_keep : 0.f;
+        const uint32_t s32 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
+        const uint32_t idx = ((uint32_t)base + (uint32_t)row) * (uint32_t)(kG / 2) + (uint32_t)(n >> 1);
+        const uint32_t h = hash32(idx * 0x9E3779B1u + s32);
+        const uint32_t t = thresh();
+        return ((h & 0xffffu) >= t ? 1u : 0u) | ((h >> 16) >= t ? 2u : 0u);
+    }
+    // v0, v1: values of packed columns (n, n+1), n even
+    __device__ __forceinline__ void apply2(float &v0, float &v1, int row, int n) const
+    {
+        if (seed == 0) return;
+        const uint32_t k = keep2(row, n);
+        const float sc = scale();
+        v0 = (k & 1u) ? v0 * sc : 0.f;
+        v1 = (k & 2u) ? v1 * sc : 0.f;
     }
 };
 
@@ -174,8 +192,8 @@ struct EpiGate {
             const int n = n0 + 2 * j;
             float t = 0.f, s = 0.f;
             if (b >= 0) {
-                float pt = drop.apply(v[2 * j] + bs[2 * j], row, n);
-                float ps = drop.apply(v[2 * j + 1] + bs[2 * j + 1], row, n + 1);
+                float pt = v[2 * j] + bs[2 * j], ps = v[2 * j + 1] + bs[2 * j + 1];
+                drop.apply2(pt, ps, row, n);
                 if (spkb != nullptr) { pt += spkb[(size_t)b * kG + n]; ps += spkb[(size_t)b * kG + n + 1]; }
                 t = tanh_t<FAST>(pt);
                 s = sigmoid_t<FAST>(ps);
@@ -334,7 +352,7 @@ struct EpiBwdGate {
         st_vec<2 * NV>(DINS + (size_t)row * kG + 2 * n0, dins);
         if (DPRE != DINS) {
 #pragma unroll
-            for (int j = 0; j < 2 * NV; ++j) dins[j] = drop.apply(dins[j], row, 2 * n0 + j);
+            for (int j = 0; j < NV; ++j) drop.apply2(dins[2 * j], dins[2 * j + 1], row, 2 * (n0 + j));
             st_vec<2 * NV>(DPRE + (size_t)row * kG + 2 * n0, dins);
         }
     }

@@ -24,6 +24,8 @@
 // CTA's epilogue overlaps the other's MMAs.
 #pragma once
 #include "flow_run.cuh"
+#include <cuda.h>
+
 #include "umma.cuh"
 
 namespace glow {
@@ -210,6 +212,251 @@ int gemm_tc(const TcA &a, const __nv_bfloat16 *Wslab, int N, int rows_pad, const
     return GLOW_OK;
 }
 
+// =====================================================================================
+// v2: persistent, warp-specialised, fully asynchronous version of the same GEMM.
+//
+//   grid = min(#items, #SMs) CTAs, item = (128-row tile, BN-column slice), static round robin.
+//   warp 0 lane 0 : A producer -- one TMA tensor-map load (cp.async.bulk.tensor.2d, box 8 x 132)
+//                   per 8-wide K chunk lands the tile's 132 rows directly in slab layout;
+//                   A panels (<= 192 columns) are double buffered, so the next item's rows
+//                   arrive while the current item's MMAs run.  Out-of-range rows are zero-filled
+//                   by the TMA unit (the conv's zero padding at the ends of the row axis).
+//   warp 2 lane 0 : B producer -- weight stages through a 4-deep ring (cp.async.bulk).
+//   warp 1 lane 0 : MMA issuer; accumulators ping-pong between two TMEM regions of BN columns.
+//   warps 3-6     : epilogue of item i overlaps the MMAs of item i+1.
+// =====================================================================================
+constexpr int kTc2Pitch = 136 * 16;              // slab pitch: 132 rows used, multiple of 128 B (TMA destination)
+constexpr int kTc2PanelBytes = 24 * kTc2Pitch;   // one A panel: up to 192 columns
+constexpr int kTc2Threads = 224;
+constexpr int kTc2Stages = 4;
+
+struct TcGeom {
+    int n_panels, kp;        // K panels per tap and their width (kp <= 192, multiple of 16)
+    int two_src;             // panel 1 comes from the second tensor map (K-concatenated sources)
+    int taps, dir;
+    int N, ks16, rows_pad, n_items, n_slices;
+    int stages;              // depth of the weight ring (2..kTc2Stages)
+};
+
+template <> struct TcShape<160> { static constexpr int kCols = 256, kChunk = 32; };
+template <int BN> struct Tc2Cols { static constexpr uint32_t value = (2 * BN <= 256) ? 256u : 512u; };
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const TcGeom g,
+                const __nv_bfloat16 *__restrict__ Wslab, const Epi epi)
+{
+    using namespace sm100;
+    constexpr int CH = TcShape<BN>::kChunk;
+    constexpr uint32_t kCols = Tc2Cols<BN>::value;
+    const int S = g.stages;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t a_full[2], a_empty[2], b_full[kTc2Stages], b_empty[kTc2Stages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kpch = g.kp >> 3;                       // 8-wide chunks per panel
+    const int per_tap = (g.kp >> 4) / g.ks16;         // weight stages per (panel, tap)
+    const int kch_all = g.n_panels * kpch;            // chunks per tap in the weight slab image
+    const uint32_t stage_bytes = (uint32_t)g.ks16 * 2u * BN * 16u;
+    const uint32_t panel_tx = (uint32_t)kpch * kTcRows * 16u;
+    unsigned char *sB = smem + 2 * kTc2PanelBytes;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
+        for (int i = 0; i < S; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tm0);
+        tma_prefetch_desc(&tm1);
+    }
+    if (warp == 1) tmem_alloc(&s_tmem, kCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {                                               // ---- A producer
+            uint32_t pc = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int row0 = (item / g.n_slices) * 128;
+                for (int p = 0; p < g.n_panels; ++p, ++pc) {
+                    const uint32_t buf = pc & 1u;
+                    if (pc >= 2) mbar_wait(&a_empty[buf], ((pc >> 1) - 1u) & 1u);
+                    mbar_arrive_expect_tx(&a_full[buf], panel_tx);
+                    const void *tm = (p == 1 && g.two_src) ? (const void *)&tm1 : (const void *)&tm0;
+                    const int col0 = (p == 1 && !g.two_src) ? g.kp : 0;
+                    unsigned char *dst = smem + buf * kTc2PanelBytes;
+                    for (int c = 0; c < kpch; ++c)
+                        tma_load_2d(dst + (size_t)c * kTc2Pitch, tm, col0 + c * 8, row0 - kGuard, &a_full[buf]);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {                                               // ---- B producer
+            uint32_t bc = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+                const int n0 = (item % g.n_slices) * BN;
+                for (int p = 0; p < g.n_panels; ++p)
+                    for (int tap = 0; tap < g.taps; ++tap)
+                        for (int st = 0; st < per_tap; ++st, ++bc) {
+                            const uint32_t slot = bc % S;
+                            if (bc >= (uint32_t)S) mbar_wait(&b_empty[slot], ((bc / S) - 1u) & 1u);
+                            mbar_arrive_expect_tx(&b_full[slot], stage_bytes);
+                            const int chunk0 = tap * kch_all + p * kpch + st * g.ks16 * 2;
+                            const __nv_bfloat16 *src = Wslab + ((size_t)chunk0 * g.N + n0) * 8;
+                            unsigned char *dst = sB + (size_t)slot * stage_bytes;
+                            for (int c = 0; c < g.ks16 * 2; ++c)
+                                bulk_g2s(dst + (size_t)c * BN * 16, src + (size_t)c * g.N * 8, BN * 16, &b_full[slot]);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                               // ---- MMA issuer
+            const uint32_t idesc = idesc_bf16_f32(128, BN);
+            const uint32_t a_base = smem_u32(smem), b_base = smem_u32(sB);
+            uint32_t pc = 0, bc = 0, it = 0;
+            for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u;
+                if (it >= 2) { mbar_wait(&acc_empty[acc], ((it >> 1) - 1u) & 1u); tc_fence_after(); }
+                const uint32_t d_tmem = tmem + acc * BN;
+                bool first = true;
+                for (int p = 0; p < g.n_panels; ++p, ++pc) {
+                    const uint32_t buf = pc & 1u;
+                    mbar_wait(&a_full[buf], (pc >> 1) & 1u);
+                    tc_fence_after();
+                    for (int tap = 0; tap < g.taps; ++tap) {
+                        const int shift = (g.taps == 1) ? kGuard : kGuard + g.dir * (tap - (kTaps - 1) / 2);
+                        for (int st = 0; st < per_tap; ++st, ++bc) {
+                            const uint32_t slot = bc % S;
+                            mbar_wait(&b_full[slot], (bc / S) & 1u);
+                            tc_fence_after();
+                            const uint32_t a_it = a_base + buf * kTc2PanelBytes + (uint32_t)shift * 16u +
+                                                  (uint32_t)(st * g.ks16 * 2) * kTc2Pitch;
+                            const uint32_t b_it = b_base + slot * stage_bytes;
+                            for (int j = 0; j < g.ks16; ++j) {
+                                const uint64_t ad = smem_desc(a_it + (uint32_t)(2 * j) * kTc2Pitch, kTc2Pitch, 128);
+                                const uint64_t bd = smem_desc(b_it + (uint32_t)(2 * j) * BN * 16u, BN * 16u, 128);
+                                umma_bf16(d_tmem, ad, bd, idesc, !first);
+                                first = false;
+                            }
+                            umma_commit(&b_empty[slot]);
+                        }
+                    }
+                    umma_commit(&a_empty[buf]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {                                                           // ---- epilogue warps 3..6
+        const int q = warp & 3;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u;
+            const int row = (item / g.n_slices) * 128 + q * 32 + lane;
+            const int n0 = (item % g.n_slices) * BN;
+            mbar_wait(&acc_full[acc], (it >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                float v[CH];
+                tmem_ld_f32<CH>(tmem + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+                epi.template apply<CH>(row, n0 + c0, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kCols);
+}
+
+// ---- host: tensor maps -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn *out)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        GLOW_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        GLOW_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, GLOW_ERR_CUDA,
+                     "cuTensorMapEncodeTiled is not available from this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    *out = fn;
+    return GLOW_OK;
+}
+
+// map over a row-major bf16 activation [rows][width] with row pitch ld; box = 8 columns x 132 rows
+static int make_act_map(CUtensorMap *tm, const __nv_bfloat16 *p, int width, int ld, int rows)
+{
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {8, (cuuint32_t)kTcRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)p, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GLOW_REQUIRE(r == CUDA_SUCCESS, GLOW_ERR_CUDA, "cuTensorMapEncodeTiled(width=%d ld=%d rows=%d) failed: %d", width,
+                 ld, rows, (int)r);
+    return GLOW_OK;
+}
+
+template <int BN, class Epi>
+int gemm_tc2(const TcA &a, const __nv_bfloat16 *Wslab, int N, int rows_pad, const Epi &epi, cudaStream_t st,
+             const char *name)
+{
+    const int Kc = a.k0 + a.k1;
+    TcGeom g;
+    g.two_src = a.k1 > 0;
+    g.n_panels = (Kc > 192) ? 2 : 1;
+    g.kp = Kc / g.n_panels;
+    GLOW_REQUIRE(N % BN == 0 && g.kp % 16 == 0 && g.kp <= 192 && rows_pad % 128 == 0 &&
+                     (!g.two_src || (a.k0 == a.k1 && g.n_panels == 2)),
+                 GLOW_ERR_INVALID, "%s: tensor-core GEMM shape N=%d BN=%d K=%d+%d rows=%d", name, N, BN, a.k0, a.k1,
+                 rows_pad);
+    const int k16 = g.kp / 16;
+    g.ks16 = (k16 % 4 == 0) ? 4 : ((k16 % 5 == 0) ? 5 : ((k16 % 3 == 0) ? 3 : 1));
+    g.taps = a.taps; g.dir = a.dir; g.N = N; g.rows_pad = rows_pad;
+    g.n_slices = N / BN;
+    g.n_items = (rows_pad / 128) * g.n_slices;
+    alignas(64) CUtensorMap tm0, tm1;
+    int rc = make_act_map(&tm0, a.p0, a.k0, a.ld0, rows_pad);
+    if (rc) return rc;
+    if (g.two_src) rc = make_act_map(&tm1, a.p1, a.k1, a.ld1, rows_pad);
+    else tm1 = tm0;
+    if (rc) return rc;
+    constexpr size_t kSmemCap = 208 * 1024;
+    const size_t stage_bytes = (size_t)g.ks16 * 2 * BN * 16;
+    g.stages = kTc2Stages;
+    while (g.stages > 2 && 2 * (size_t)kTc2PanelBytes + g.stages * stage_bytes > kSmemCap) --g.stages;
+    const size_t smem = 2 * (size_t)kTc2PanelBytes + (size_t)g.stages * stage_bytes;
+    GLOW_REQUIRE(smem <= kSmemCap, GLOW_ERR_UNSUPPORTED, "%s: %zu B of shared memory", name, smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GLOW_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kSmemCap));
+        attr_set = true;
+    }
+    const int grid = g.n_items < kNumSMs ? g.n_items : kNumSMs;
+    ProfScope prof(name, st);
+    tc_gemm2_kernel<BN, Epi><<<grid, kTc2Threads, smem, st>>>(tm0, tm1, g, Wslab, epi);
+    GLOW_CHECK_LAUNCH(name);
+    return GLOW_OK;
+}
+
 // ------------------------------------------------------------------ tensor-core ops --
 template <bool FAST>
 struct TcOps {
@@ -222,7 +469,7 @@ struct TcOps {
     static int start(const Ctx &c, int k, const Bufs<ActT> &b)
     {
         EpiStart<ActT> e{wp(c, k) + c.bp.start_b, b.H[0], c.rows.row_utt};
-        return gemm_tc<96>(rows(b.YA, kCh, kCh), ws(c, k) + c.bt.start_w, kH, c.rows.rows_pad, e, c.st, "start");
+        return gemm_tc2<192>(rows(b.YA, kCh, kCh), ws(c, k) + c.bt.start_w, kH, c.rows.rows_pad, e, c.st, "start");
     }
     static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
     {
@@ -230,42 +477,42 @@ struct TcOps {
         TcA a{b.H[i], nullptr, kH, 0, kH, 0, kTaps, +1};
         EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
                                drop_cfg(c, k, i)};
-        int rc = gemm_tc<192>(a, ws(c, k) + c.bt.in_w[i], kG, c.rows.rows_pad, eg, c.st, "in_gate");
+        int rc = gemm_tc2<192>(a, ws(c, k) + c.bt.in_w[i], kG, c.rows.rows_pad, eg, c.st, "in_gate");
         if (rc) return rc;
         EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
                             c.rows.row_utt, i == 0, last};
-        if (last) return gemm_tc<96>(rows(b.ACTS[i], kH, kH), ws(c, k) + c.bt.rs_w[i], kH, c.rows.rows_pad, er, c.st, "res_skip");
-        return gemm_tc<192>(rows(b.ACTS[i], kH, kH), ws(c, k) + c.bt.rs_w[i], kG, c.rows.rows_pad, er, c.st, "res_skip");
+        if (last) return gemm_tc2<192>(rows(b.ACTS[i], kH, kH), ws(c, k) + c.bt.rs_w[i], kH, c.rows.rows_pad, er, c.st, "res_skip");
+        return gemm_tc2<192>(rows(b.ACTS[i], kH, kH), ws(c, k) + c.bt.rs_w[i], kG, c.rows.rows_pad, er, c.st, "res_skip");
     }
     static int end(const Ctx &c, int k, const Bufs<ActT> &b, const EpiEnd<ActT, FAST> &e)
     {
-        return gemm_tc<80>(rows(b.OUT, kH, kH), ws(c, k) + c.bt.end_w, kC, c.rows.rows_pad, e, c.st, "end");
+        return gemm_tc2<160>(rows(b.OUT, kH, kH), ws(c, k) + c.bt.end_w, kC, c.rows.rows_pad, e, c.st, "end");
     }
     // backward
     static int b_end(const Ctx &c, int k, const ActT *DOUTS, ActT *DOUT)
     {
         EpiBwdEnd<ActT> e{DOUT, c.rows.row_utt};
-        return gemm_tc<96>(rows(DOUTS, kC, kC), ws(c, k) + c.bt.end_wt, kH, c.rows.rows_pad, e, c.st, "b_end");
+        return gemm_tc2<192>(rows(DOUTS, kC, kC), ws(c, k) + c.bt.end_wt, kH, c.rows.rows_pad, e, c.st, "b_end");
     }
     static int b_rs(const Ctx &c, int k, int i, const Bufs<ActT> &b, const ActT *DHnext, const ActT *DOUT,
                     ActT *DINS, ActT *DPRE)
     {
         EpiBwdGate<ActT> e{b.TS[i], DINS, DPRE, c.rows.row_utt, drop_cfg(c, k, i)};
         if (i == kLayers - 1)
-            return gemm_tc<96>(rows(DOUT, kH, kH), ws(c, k) + c.bt.rs_wt[i], kH, c.rows.rows_pad, e, c.st, "b_rs");
+            return gemm_tc2<192>(rows(DOUT, kH, kH), ws(c, k) + c.bt.rs_wt[i], kH, c.rows.rows_pad, e, c.st, "b_rs");
         TcA a{DHnext, DOUT, kH, kH, kH, kH, 1, 0};
-        return gemm_tc<96>(a, ws(c, k) + c.bt.rs_wt[i], kH, c.rows.rows_pad, e, c.st, "b_rs");
+        return gemm_tc2<192>(a, ws(c, k) + c.bt.rs_wt[i], kH, c.rows.rows_pad, e, c.st, "b_rs");
     }
     static int b_in(const Ctx &c, int k, int i, const ActT *DPRE, const ActT *DHnext, ActT *DH)
     {
         TcA a{DPRE, nullptr, kG, 0, kG, 0, kTaps, -1};
         EpiBwdIn<ActT> e{DHnext, DH, c.rows.row_utt};
-        return gemm_tc<96>(a, ws(c, k) + c.bt.in_wt[i], kH, c.rows.rows_pad, e, c.st, "b_in");
+        return gemm_tc2<192>(a, ws(c, k) + c.bt.in_wt[i], kH, c.rows.rows_pad, e, c.st, "b_in");
     }
     static int b_start(const Ctx &c, int k, const ActT *DH0, float *DY)
     {
         EpiBwdStart e{DY};
-        return gemm_tc<80>(rows(DH0, kH, kH), ws(c, k) + c.bt.start_wt, kCh, c.rows.rows_pad, e, c.st, "b_start");
+        return gemm_tc2<80>(rows(DH0, kH, kH), ws(c, k) + c.bt.start_wt, kCh, c.rows.rows_pad, e, c.st, "b_start");
     }
 };
 

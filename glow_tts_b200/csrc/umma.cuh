@@ -68,6 +68,21 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
         : "memory");
 }
 
+// 2-D tiled tensor-map load (TMA): box of the map at element coordinates (c0 = inner, c1 = outer);
+// out-of-range rows / columns arrive as zeros.  smem_dst must be 128 B aligned.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 --
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t ncols)   // one full warp
 {

@@ -127,3 +127,51 @@ def test_tensor_core_path_matches_cuda_core_path(mode, tls, mls):
     assert float((back1 - back2).abs().mean() / back2.abs().mean()) < 3e-2
     worst = max((rel_err(g1[k], g2[k]), k) for k in g1 if float(g2[k].abs().max()) > 0)
     assert worst[0] < 6e-2, worst
+
+
+def test_training_dropout_masks_agree_between_forward_and_backward():
+    """Dropout on the gate pre-activation (Modules.py:862) is counter-based in the kernels: backward
+    recomputes the forward's keep mask.  With the dropout stream pinned, the analytic gradient must
+    equal a central finite difference of the (deterministic) forward -- fp32 mode, p = 0.3 so a
+    mask mismatch would be a >10% error; tolerance 2e-2."""
+    from glow_tts_b200 import modules
+    from glow_tts_b200.hparams import load_hparams
+    from tests._util import synth_batch, synth_state_dict
+    modules.set_hparams(load_hparams(Mode="Vanilla", Precision="fp32",
+                                     **{"Decoder.Affine_Coupling.WaveNet.Dropout_Rate": 0.3, "Decoder.Stack": 4}))
+    model = modules.GlowTTS()
+    model.load_state_dict(synth_state_dict(model.state_dict(), 5), strict=True)
+    for blk in model.layer_Dict["Decoder"].layer_Dict["Flows"]:
+        blk.layers[0].initialized = True
+    model = model.cuda()
+    model.train()
+    dec = model.layer_Dict["Decoder"]
+    tokens, tl, mels, ml, spk = synth_batch(3, [20, 12], [120, 64])
+    x, m = mels.cuda(), mel_mask(ml, "cuda")
+    gen = torch.Generator().manual_seed(1)
+    rz = torch.randn(x.shape, generator=gen).cuda()
+    rl = torch.randn(len(ml), generator=gen).cuda()
+
+    def loss():
+        dec._step = 41                                   # same dropout stream on every call
+        z, ld, _ = dec(x, m, None)
+        return (z * rz).sum() + (ld * rl).sum()
+
+    model.zero_grad(set_to_none=True)
+    base = loss()
+    base.backward()
+    params = [p for p in dec.parameters() if p.grad is not None]
+    dirs = [torch.randn(p.shape, generator=gen).cuda() * p.detach().abs().mean() for p in params]
+    dot = float(sum((p.grad.double() * d.double()).sum() for p, d in zip(params, dirs)))
+    with torch.no_grad():
+        again = loss()
+        assert float((again - base).abs()) <= 1e-5 * float(base.abs())       # deterministic given the seed
+        eps = 2e-3
+        for p, d in zip(params, dirs):
+            p.add_(eps * d)
+        lp = float(loss().double())
+        for p, d in zip(params, dirs):
+            p.sub_(2 * eps * d)
+        lm = float(loss().double())
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - dot) <= 2e-2 * abs(dot), (fd, dot)

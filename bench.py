@@ -240,10 +240,13 @@ def run_own(args):
     pinned = (tokens.pin_memory(), tl, mels.pin_memory(), ml, spk.pin_memory())
     real = int(ml.sum())
     padded = int(mels.shape[0] * mels.shape[2])
-    counts = torch.tensor([float(real), float(tokens.numel()), float(padded)], device=dev)
+    counts = torch.tensor([float(real), float(tokens.shape[0]), float(padded)], device=dev)
+    tmax = torch.tensor([float(tokens.shape[1])], device=dev)
     if world > 1:
         dist.all_reduce(counts)
-    g_frames, g_pos, g_padded = (int(v) for v in counts.tolist())
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    g_frames, g_batch, g_padded = (int(v) for v in counts.tolist())
+    g_pos = g_batch * int(tmax)                       # B * T_x,max of the global batch (what MSELoss averages over)
     dev_batch = step.to_device(pinned)
 
     def one_step(b):

@@ -64,6 +64,7 @@ SIGNATURES = {
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_sqnorm": (_I, [_P, _Z, _P, _P]),
     "glow_radam_step": (_I, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _F, _F, _P, _P, _P]),
+    "glow_selftest_umma_mn": (_I, [_P, _P, _P, _I, _I, _U32, _U32, _P]),
     "glow_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _U32, _U32, _U32, _U32, _I, _P]),
 }
 

@@ -25,6 +25,7 @@
 #pragma once
 #include "flow_run.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "umma.cuh"
 
@@ -236,6 +237,7 @@ struct TcGeom {
     int taps, dir;
     int N, ks16, rows_pad, n_items, n_slices;
     int stages;              // depth of the weight ring (2..kTc2Stages)
+    long long *dbg;          // optional timeline of CTA 0 (GLOW_TC_DEBUG=1), else null
 };
 
 template <> struct TcShape<160> { static constexpr int kCols = 256, kChunk = 32; };
@@ -277,6 +279,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    long long *dbg = (blockIdx.x == 0) ? g.dbg : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {                                               // ---- A producer
@@ -328,12 +332,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
                     const uint32_t buf = pc & 1u;
                     mbar_wait(&a_full[buf], (pc >> 1) & 1u);
                     tc_fence_after();
+                    if (dbg && it < 2 && p == 0) dbg[16 + it * 40] = clock64();
                     for (int tap = 0; tap < g.taps; ++tap) {
                         const int shift = (g.taps == 1) ? kGuard : kGuard + g.dir * (tap - (kTaps - 1) / 2);
                         for (int st = 0; st < per_tap; ++st, ++bc) {
                             const uint32_t slot = bc % S;
                             mbar_wait(&b_full[slot], (bc / S) & 1u);
                             tc_fence_after();
+                            if (dbg && it < 2 && p == 0 && tap * per_tap + st < 36) dbg[16 + it * 40 + 1 + tap * per_tap + st] = clock64();
                             const uint32_t a_it = a_base + buf * kTc2PanelBytes + (uint32_t)shift * 16u +
                                                   (uint32_t)(st * g.ks16 * 2) * kTc2Pitch;
                             const uint32_t b_it = b_base + slot * stage_bytes;
@@ -349,6 +355,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
                     umma_commit(&a_empty[buf]);
                 }
                 umma_commit(&acc_full[acc]);
+                if (dbg && it < 2) dbg[16 + it * 40 + 38] = clock64();
             }
         }
     } else {                                                           // ---- epilogue warps 3..6
@@ -360,20 +367,27 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
             const int n0 = (item % g.n_slices) * BN;
             mbar_wait(&acc_full[acc], (it >> 1) & 1u);
             tc_fence_after();
+            if (dbg && it < 2 && warp == 3 && lane == 0) dbg[100 + it * 4] = clock64();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CH) {
                 float v[CH];
+                const bool rec = dbg && it == 0 && warp == 3 && lane == 0 && c0 / CH < 6;
+                if (rec) dbg[108 + 3 * (c0 / CH)] = clock64();
                 tmem_ld_f32<CH>(tmem + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+                if (rec) dbg[109 + 3 * (c0 / CH)] = clock64();
                 epi.template apply<CH>(row, n0 + c0, v);
+                if (rec) dbg[110 + 3 * (c0 / CH)] = clock64();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (dbg && it < 2 && warp == 3 && lane == 0) dbg[100 + it * 4 + 1] = clock64();
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kCols);
+    if (dbg && tid == 0) dbg[1] = clock64();
 }
 
 // ---- host: tensor maps -----------------------------------------------------------------
@@ -451,9 +465,40 @@ int gemm_tc2(const TcA &a, const __nv_bfloat16 *Wslab, int N, int rows_pad, cons
         attr_set = true;
     }
     const int grid = g.n_items < kNumSMs ? g.n_items : kNumSMs;
-    ProfScope prof(name, st);
-    tc_gemm2_kernel<BN, Epi><<<grid, kTc2Threads, smem, st>>>(tm0, tm1, g, Wslab, epi);
-    GLOW_CHECK_LAUNCH(name);
+    g.dbg = nullptr;
+    static int dbg_left = getenv("GLOW_TC_DEBUG") ? 3 : 0;      // per instantiation: first 3 launches
+    static long long *dbg_buf = nullptr;
+    const bool dbg_on = dbg_left > 0;
+    if (dbg_on) {
+        if (!dbg_buf) GLOW_CHECK_CUDA(cudaMalloc(&dbg_buf, 128 * sizeof(long long)));
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), st));
+        g.dbg = dbg_buf;
+        --dbg_left;
+    }
+    {
+        ProfScope prof(name, st);
+        tc_gemm2_kernel<BN, Epi><<<grid, kTc2Threads, smem, st>>>(tm0, tm1, g, Wslab, epi);
+        GLOW_CHECK_LAUNCH(name);
+    }
+    if (dbg_on) {
+        long long h[128];
+        GLOW_CHECK_CUDA(cudaStreamSynchronize(st));
+        GLOW_CHECK_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[tc-debug] %s grid=%d items=%d panels=%d kp=%d taps=%d ks16=%d stages=%d | end=%lld\n", name, grid,
+                g.n_items, g.n_panels, g.kp, g.taps, g.ks16, g.stages, h[1] - h[0]);
+        for (int it = 0; it < 2; ++it) {
+            if (!h[16 + it * 40]) continue;
+            fprintf(stderr, "[tc-debug]   item %d: a_full=%lld  b_full:", it, h[16 + it * 40] - h[0]);
+            for (int i = 0; i < 36; ++i)
+                if (h[16 + it * 40 + 1 + i]) fprintf(stderr, " %lld", h[16 + it * 40 + 1 + i] - h[0]);
+            fprintf(stderr, "  mma_issued=%lld  epi_start=%lld epi_end=%lld\n", h[16 + it * 40 + 38] - h[0],
+                    h[100 + it * 4] - h[0], h[100 + it * 4 + 1] - h[0]);
+        }
+        fprintf(stderr, "[tc-debug]   item 0 epilogue chunks (ld_start, ld_done, apply_done):");
+        for (int c = 0; c < 6; ++c)
+            if (h[108 + 3 * c]) fprintf(stderr, " [%lld %lld %lld]", h[108 + 3 * c] - h[0], h[109 + 3 * c] - h[0], h[110 + 3 * c] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return GLOW_OK;
 }
 

@@ -81,7 +81,71 @@ umma_probe_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__re
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// MN-major variant: C[128, N] = sum_r A[r, m] * D[r, n], both operands given "chunk-major"
+// ([cols/8][R][8] bf16: for one reduction index r, 8 consecutive columns are one 16 B vector and
+// consecutive r are consecutive vectors -- exactly the 8 x 16 B core matrices of the MN-major
+// SWIZZLE_NONE layout).  This is the operand form of the weight-gradient GEMMs, whose reduction
+// runs over the packed row axis.  lbo / sbo from the caller, as above.
+__global__ void __launch_bounds__(128)
+umma_probe_mn_kernel(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ D, float *__restrict__ C,
+                     int R, int N, uint32_t lbo, uint32_t sbo)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_mma;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t plane = (uint32_t)R * 16u;
+    unsigned char *sA = smem;                          // [128/8][R][16 B]
+    unsigned char *sD = smem + 16 * plane;             // [N/8][R][16 B]
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_fence_init(); }
+    for (int i = tid; i < 16 * R; i += 128) reinterpret_cast<uint4 *>(sA)[i] = reinterpret_cast<const uint4 *>(A)[i];
+    for (int i = tid; i < (N / 8) * R; i += 128) reinterpret_cast<uint4 *>(sD)[i] = reinterpret_cast<const uint4 *>(D)[i];
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        const uint32_t idesc = idesc_bf16_f32(128, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+        for (int j = 0; j < R / 16; ++j) {
+            const uint64_t ad = smem_desc(smem_u32(sA) + (uint32_t)j * 256u, lbo, sbo);
+            const uint64_t bd = smem_desc(smem_u32(sD) + (uint32_t)j * 256u, lbo, sbo);
+            umma_bf16(tmem, ad, bd, idesc, j > 0);
+        }
+        umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        float *dst = C + (size_t)(warp * 32 + lane) * N + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace glow
+
+extern "C" int glow_selftest_umma_mn(const void *a, const void *d, float *c, int r, int n, uint32_t lbo, uint32_t sbo,
+                                     glow_stream_t stream)
+{
+    using namespace glow;
+    GLOW_REQUIRE(a && d && c, GLOW_ERR_INVALID, "selftest_umma_mn: null pointer");
+    GLOW_REQUIRE(r % 16 == 0 && r >= 16 && n % 32 == 0 && n >= 32 && n <= 256, GLOW_ERR_INVALID,
+                 "selftest_umma_mn: need r%%16==0, n%%32==0, n<=256");
+    const size_t smem = (size_t)(16 + n / 8) * r * 16;
+    GLOW_REQUIRE(smem <= 200 * 1024, GLOW_ERR_UNSUPPORTED, "selftest_umma_mn: %zu B smem", smem);
+    GLOW_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_probe_mn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, (const __nv_bfloat16 *)d, c, r,
+                                                                n, lbo, sbo);
+    GLOW_CHECK_LAUNCH("umma_probe_mn_kernel");
+    return GLOW_OK;
+}
 
 extern "C" int glow_selftest_umma(const void *a, const void *b_packed, float *d, int rows_a, int k, int n,
                                   int shift, uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b,

@@ -55,6 +55,24 @@ class FusedRAdam:
         self.epoch += 1         # scheduler.step() (Train.py:233)
 
 
+def ddp_loss_weights(local_frames, local_positions, world, global_frames, global_positions):
+    """Weights that make the data-parallel step reproduce the single-process global-batch loss.
+
+    MLE_Loss divides by the LOCAL batch's frame count (Modules.py:1026) and MSELoss averages over the
+    LOCAL B*T_x,max positions (Train.py:210), so a plain mean of per-rank losses is not the loss of the
+    concatenated batch when shards are ragged.  With gradients SUMMED by the all-reduce and scaled by
+    1/world afterwards (FusedRAdam.step(grad_scale=1/world)), rank r's terms must carry
+    local/global * world.  Returns (w_mle, w_mse)."""
+    return (local_frames * world / float(global_frames), local_positions * world / float(global_positions))
+
+
+def shard_slice(n_items, rank, world):
+    """Contiguous utterance shard of rank `rank`: items [lo, hi)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
 class TrainStep:
     """Owns the model's flat buffers and the optimizer; `run(batch)` is one Train_Step."""
 
@@ -95,8 +113,7 @@ class TrainStep:
         mse = F.mse_loss(log_dur, log_dur_t)
         if self.world > 1:
             local_frames = sum(n // 2 * 2 for n in ml_h)
-            w_mle = local_frames * self.world / float(global_frames)
-            w_mse = log_dur.numel() * self.world / float(global_positions)
+            w_mle, w_mse = ddp_loss_weights(local_frames, log_dur.numel(), self.world, global_frames, global_positions)
             # constant 0.5*log(2*pi) keeps its weight 1 (no gradient, reporting only)
             loss = (mle - 0.5 * math.log(2 * math.pi)) * w_mle + 0.5 * math.log(2 * math.pi) + mse * w_mse
         else:

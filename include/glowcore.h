@@ -236,6 +236,11 @@ int glow_selftest_umma(const void *a, const void *b_packed, float *d,
                        uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b,
                        int use_bulk, glow_stream_t stream);
 
+/* Same for MN-major operands (the weight-gradient form): c[128,n] f32 = sum over r of
+ * a[r, 0..127] * d[r, 0..n-1], with a and d given chunk-major ([cols/8][r][8] bf16). */
+int glow_selftest_umma_mn(const void *a, const void *d, float *c, int r, int n,
+                          uint32_t lbo, uint32_t sbo, glow_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

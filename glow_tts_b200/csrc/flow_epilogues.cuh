@@ -168,7 +168,12 @@ struct EpiStart {
     const float *bias; ActT *H; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const bool m = row_utt[row] >= 0;
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const bool m = utt >= 0;
         float b[NV], out[NV];
         ld_vec<NV>(bias + n0, b);
 #pragma unroll
@@ -184,7 +189,12 @@ struct EpiGate {
     const float *bias; const float *spkb; ActT *TS; ActT *ACTS; const int32_t *row_utt; DropCfg drop;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const int b = row_utt[row];
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const int b = utt;
         float bs[NV], ts[NV], acts[NV / 2];
         ld_vec<NV>(bias + n0, bs);
 #pragma unroll
@@ -214,8 +224,13 @@ struct EpiResSkip {
     int first, last;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
         // n0 is a multiple of NV and NV divides kH, so the NV columns lie on one side of the res | skip split
-        const bool m = row_utt[row] >= 0;
+        const bool m = utt >= 0;
         float b[NV], out[NV], old[NV];
         ld_vec<NV>(bias + n0, b);
         if (last) {
@@ -259,7 +274,12 @@ struct EpiEnd {
     int reverse;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const bool m = row_utt[row] >= 0;
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const bool m = utt >= 0;
         const int c0 = n0 >> 1;
         float za[NV / 2], zb[NV / 2], bs[NV], outs[NV], oa[NV / 2], ob[NV / 2];
         float ld = 0.f;
@@ -325,7 +345,12 @@ struct EpiBwdEnd {
     ActT *DOUT; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const bool m = row_utt[row] >= 0;
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const bool m = utt >= 0;
         float out[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) out[j] = m ? v[j] : 0.f;
@@ -340,7 +365,12 @@ struct EpiBwdGate {
     const ActT *TS; ActT *DINS; ActT *DPRE; const int32_t *row_utt; DropCfg drop;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const bool m = row_utt[row] >= 0;
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const bool m = utt >= 0;
         float ts[2 * NV], dins[2 * NV];
         ld_vec<2 * NV>(TS + (size_t)row * kG + 2 * n0, ts);
 #pragma unroll
@@ -364,7 +394,12 @@ struct EpiBwdIn {
     const ActT *DHnext; ActT *DH; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
-        const bool m = row_utt[row] >= 0;
+        apply_u<NV>(row, row_utt[row], n0, v);
+    }
+    // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        const bool m = utt >= 0;
         const size_t o = (size_t)row * kH + n0;
         float r[NV], out[NV];
         if (DHnext != nullptr) ld_vec<NV>(DHnext + o, r);
@@ -377,6 +412,10 @@ struct EpiBwdIn {
 // d(y_a) += d(h0) W_start
 struct EpiBwdStart {
     float *DY;
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int, int n0, const float *v) const
+    {
+        apply<NV>(row, n0, v);
+    }
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         float old[NV];

@@ -82,6 +82,7 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
     jobs->count = 0;
     int cta = 0;
     small->blocks = cfg.blocks;
+    auto slice_of = [](int n) { return n == kG ? kBnGate : n == kH ? kBnH : n == kC ? kBnEnd : kBnHalf; };
     auto add = [&](const int64_t *o, int sb, int sg, int sv, int n_out, int k_in, int taps, int il, float *wp,
                    const float *dwp, size_t W, size_t WT, size_t B, __nv_bfloat16 *tp, size_t sW, size_t sWT,
                    bool has_tc) {
@@ -100,6 +101,8 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
         j.dg = (grads && sg >= 0) ? grads + o[sg] : nullptr;
         j.db = grads ? grads + o[sb] : nullptr;
         j.n_out = n_out; j.k_in = k_in; j.taps = taps; j.interleave = il;
+        j.bn_w = has_tc ? slice_of(n_out) : n_out;
+        j.bn_wt = has_tc ? slice_of(k_in) : k_in;
         j.cta_begin = cta;
         cta += n_out;
     };

@@ -16,6 +16,7 @@ struct WnJob {
     const float *dW, *dbpack;        // grads of effective weights (grad job)
     float *dv, *dg, *db;             // flat-gradient destinations (grad job)
     int n_out, k_in, taps, interleave;
+    int bn_w, bn_wt;                 // column slice of the slabW (N = n_out) / slabWT (N = k_in) images
     int cta_begin;
 };
 struct WnJobs {

@@ -25,6 +25,26 @@ constexpr int kLayers = 4;     // WaveNet layers
 constexpr int kGuard = 2;      // (kTaps-1)/2 zero rows between utterances
 constexpr int kRowTile = 128;  // rows_pad is a multiple of this
 
+// Output-column slice per work item of the tcgen05 GEMMs (flow_tc.cuh), by GEMM output width.
+// The bf16 weight slab images are laid out per slice, so glow_flow_prepare and the kernels share them.
+#ifndef GLOW_BN_GATE
+#define GLOW_BN_GATE 128
+#endif
+#ifndef GLOW_BN_H
+#define GLOW_BN_H 192
+#endif
+#ifndef GLOW_BN_END
+#define GLOW_BN_END 160
+#endif
+#ifndef GLOW_TC_KS
+#define GLOW_TC_KS 96
+#endif
+constexpr int kBnGate = GLOW_BN_GATE;   // N = 384 (gate pre-activations, res|skip)
+constexpr int kBnH = GLOW_BN_H;         // N = 192
+constexpr int kBnEnd = GLOW_BN_END;     // N = 160 (End: interleaved mean, logs)
+constexpr int kBnHalf = kCh;            // N = 80
+constexpr int kTcKs = GLOW_TC_KS;       // K per weight stage for the K = 192 panels
+
 struct FlowCfg {               // == glow_flow_config (include/glowcore.h)
     int blocks, channels, hidden, layers, kernel, split, spk_dim;
     float dropout;
@@ -77,7 +97,8 @@ inline BlockPack make_block_pack(int spk_dim)
 }
 
 // ---- bf16 "slab" images of the same weights for the tcgen05 path -------------
-// slab image of a [K][N] weight: [K/8][N][8] bf16 (see csrc/umma.cuh smem_desc).
+// slab image of a [taps][K][N] weight, N cut into slices of BN columns:
+//   [N/BN][taps][K/8][BN][8] bf16 (see csrc/umma.cuh smem_desc) -- a (slice, tap, K-range) stage is contiguous.
 struct BlockPackTC {           // element offsets (bf16) inside one block's bf16 region
     size_t start_w, start_wt;                 // K=80,N=192 ; K=192,N=80
     size_t in_w[kLayers], in_wt[kLayers];     // per tap: K=192,N=384 ; K=384,N=192

@@ -20,8 +20,8 @@ __device__ __forceinline__ int pack_col(int n, int n_out, bool interleave)
 
 // One CTA per output channel n.  v: [n_out][k_in][taps], g: [n_out] or null (plain conv).
 // Writes W[(tap*k_in + k)][n'] , WT[(tap*n_out + n')][k] fp32 and optional bf16 slab images
-//   slabW [tap][k_in/8][n_out][8]   (B operand of the forward GEMM,  N = n_out, K = k_in)
-//   slabWT[tap][n_out/8][k_in][8]   (B operand of the data-grad GEMM, N = k_in, K = n_out)
+//   slabW [n_out/bn_w][tap][k_in/8][bn_w][8]    (B operand of the forward GEMM,  N = n_out, K = k_in)
+//   slabWT[k_in/bn_wt][tap][n_out/8][bn_wt][8]  (B operand of the data-grad GEMM, N = k_in, K = n_out)
 __device__ __forceinline__ const WnJob &find_job(const WnJobs &jobs, int cta)
 {
     int lo = 0, hi = jobs.count - 1;
@@ -40,6 +40,7 @@ wn_pack_kernel(const __grid_constant__ WnJobs jobs)
     float *__restrict__ W = J.W, *__restrict__ WT = J.WT, *__restrict__ bpack = J.bpack;
     __nv_bfloat16 *__restrict__ slabW = J.slabW, *__restrict__ slabWT = J.slabWT;
     const int n_out = J.n_out, k_in = J.k_in, taps = J.taps, interleave = J.interleave;
+    const int bn_w = J.bn_w, bn_wt = J.bn_wt;
     const int n = blockIdx.x - J.cta_begin, tid = threadIdx.x;
     const int per = k_in * taps;
     const float *vn = v + (size_t)n * per;
@@ -63,8 +64,8 @@ wn_pack_kernel(const __grid_constant__ WnJobs jobs)
         if (WT != nullptr) WT[((size_t)tap * n_out + np) * k_in + k] = w;
         if (slabW != nullptr) {
             const __nv_bfloat16 wb = __float2bfloat16(w);
-            slabW[(((size_t)tap * (k_in / 8) + k / 8) * n_out + np) * 8 + (k & 7)] = wb;
-            slabWT[(((size_t)tap * (n_out / 8) + np / 8) * k_in + k) * 8 + (np & 7)] = wb;
+            slabW[((((size_t)(np / bn_w) * taps + tap) * (k_in / 8) + k / 8) * bn_w + np % bn_w) * 8 + (k & 7)] = wb;
+            slabWT[((((size_t)(k / bn_wt) * taps + tap) * (n_out / 8) + np / 8) * bn_wt + k % bn_wt) * 8 + (np & 7)] = wb;
         }
     }
 }

@@ -46,6 +46,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin)
         if (mbar_try_wait(bar, parity)) return;
     __trap();

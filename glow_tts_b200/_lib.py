@@ -25,7 +25,7 @@ class FlowConfig(ctypes.Structure):          # glow_flow_config
 
 class FlowCall(ctypes.Structure):            # glow_flow_call
     _fields_ = [("cfg", FlowConfig), ("precision", _I), ("batch", _I), ("t_max", _I), ("rows_pad", _I),
-                ("training", _I), ("seed", _U64),
+                ("training", _I), ("seed", _U64), ("step_dev", _P),
                 ("row_utt", _P), ("row_t", _P), ("utt_off", _P), ("utt_len", _P),
                 ("wpack", _P), ("wpack_tc", _P), ("spk", _P),
                 ("ws_f32", _P), ("ws_act", _P), ("bw_f32", _P), ("bw_act", _P), ("stream", _P)]
@@ -34,7 +34,7 @@ class FlowCall(ctypes.Structure):            # glow_flow_call
 class AttnCall(ctypes.Structure):            # glow_attn_call
     _fields_ = [("q", _P), ("k", _P), ("v", _P), ("wk", _P), ("wv", _P), ("lengths", _P), ("mask", _P),
                 ("batch", _I), ("heads", _I), ("t", _I), ("head_dim", _I), ("window", _I),
-                ("dropout", _F), ("seed", _U64), ("stream", _P)]
+                ("dropout", _F), ("seed", _U64), ("step_dev", _P), ("stream", _P)]
 
 
 _PCFG, _PCALL, _PATTN = ctypes.POINTER(FlowConfig), ctypes.POINTER(FlowCall), ctypes.POINTER(AttnCall)
@@ -64,6 +64,7 @@ SIGNATURES = {
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_sqnorm": (_I, [_P, _Z, _P, _P]),
     "glow_radam_step": (_I, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _F, _F, _P, _P, _P]),
+    "glow_radam_step_dev": (_I, [_P, _P, _P, _P, _Z, _P, _P, _P, _P]),
     "glow_selftest_umma_mn": (_I, [_P, _P, _P, _I, _I, _U32, _U32, _P]),
     "glow_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _U32, _U32, _U32, _U32, _I, _P]),
 }
@@ -112,6 +113,44 @@ def require_cuda(t, name):
         raise GlowCoreError(
             "%s must live on a CUDA device: glow_tts_b200 runs only on the sm_100a kernels "
             "in libglowcore.so (no CPU fallback)" % name)
+
+
+# ---- device step counter (dropout under CUDA-graph replay) -------------------------------
+# One int64 per device, owned by whoever drives training (train.TrainStep).  When registered,
+# every flow / attention call hands its address to the kernels, which mix *counter into their
+# dropout seed: a call captured in a CUDA graph then draws fresh masks on every replay.
+_STEP_COUNTERS = {}
+
+
+def set_step_counter(device, tensor):
+    key = str(torch.device(device))
+    if tensor is None:
+        _STEP_COUNTERS.pop(key, None)
+    else:
+        assert tensor.dtype == torch.int64 and tensor.numel() == 1 and tensor.is_cuda
+        _STEP_COUNTERS[key] = tensor
+
+
+def step_counter_ptr(device):
+    t = _STEP_COUNTERS.get(str(torch.device(device)))
+    return None if t is None else t.data_ptr()
+
+
+# ---- small host lists -> cached device tensors ---------------------------------------------
+# Lengths come from the host collater; turning them into device tensors is an H2D copy from
+# pageable memory, which is a sync point and illegal inside CUDA-graph capture.  Steps that see
+# the same lengths again (a captured step does, by construction) reuse the device copy.
+_DEV_INTS = {}
+
+
+def device_ints(values, dtype, device):
+    key = (tuple(int(v) for v in values), dtype, str(torch.device(device)))
+    t = _DEV_INTS.get(key)
+    if t is None:
+        if len(_DEV_INTS) > 512:
+            _DEV_INTS.clear()
+        t = _DEV_INTS[key] = torch.tensor(list(key[0]), dtype=dtype).to(device)
+    return t
 
 
 def launch_count():

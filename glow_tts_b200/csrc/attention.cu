@@ -40,6 +40,7 @@ struct AttnArgs {
     int B, H, T, window;
     float scale, drop_p;
     uint64_t seed;                 // 0: no dropout
+    const uint64_t *step_dev;      // optional device step counter mixed into seed (CUDA-graph replays)
     // forward outputs
     float *out;                    // [B, H*d, T]
     float *probs;                  // [B,H,T,T] softmax before dropout (saved for backward) or null
@@ -50,6 +51,13 @@ struct AttnArgs {
     float *dwk, *dwv;              // [2w+1, d], accumulated with atomics (caller zeroes)
     float *ds;                     // [B,H,T,T] scratch: scale * dS
 };
+
+// dropout seed of this launch: the by-value seed, mixed with the device step counter when one is given
+__device__ __forceinline__ uint64_t attn_seed(const AttnArgs &a)
+{
+    if (a.seed == 0 || a.step_dev == nullptr) return a.seed;
+    return (a.seed ^ (__ldg(a.step_dev) * 0xD6E8FEB86659FD93ull)) | 1ull;
+}
 
 // tile[i][e] <- src[b, h*d + e, i0 + i]   (coalesced along time); rows beyond T read 0
 __device__ __forceinline__ void load_tile_T(float (*tile)[kAD + 1], const float *src, int b, int h, int H, int T,
@@ -183,6 +191,7 @@ static size_t attn_smem_bytes(int T)
 __global__ void __launch_bounds__(kAThreads)
 rpr_attn_fwd_kernel(const AttnArgs a)
 {
+    const uint64_t seed = attn_seed(a);
     extern __shared__ __align__(16) unsigned char raw[];
     AttnSmem sm = carve(raw, a.T);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,7 +224,7 @@ rpr_attn_fwd_kernel(const AttnArgs a)
             const float p = row[j] * inv;
             if (a.probs != nullptr) a.probs[base + j] = p;
             float pd = p;
-            if (a.seed != 0) pd = attn_keep(a.seed, base + j, a.drop_p) ? p * inv_keep : 0.f;   // :120
+            if (seed != 0) pd = attn_keep(seed, base + j, a.drop_p) ? p * inv_keep : 0.f;   // :120
             if (a.align != nullptr) a.align[base + j] = pd;
             row[j] = pd;
         }
@@ -230,6 +239,7 @@ rpr_attn_fwd_kernel(const AttnArgs a)
 __global__ void __launch_bounds__(kAThreads)
 rpr_attn_bwd_q_kernel(const AttnArgs a)
 {
+    const uint64_t seed = attn_seed(a);
     extern __shared__ __align__(16) unsigned char raw[];
     AttnSmem sm = carve(raw, a.T);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -250,7 +260,7 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
             if (gi < T && j >= 0 && j < T) {
                 const size_t idx = ((size_t)(b * a.H + h) * T + gi) * T + j;
                 float pd = a.probs[idx];
-                if (a.seed != 0) pd = attn_keep(a.seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
+                if (seed != 0) pd = attn_keep(seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
                 acc = fmaf(pd, sm.As[i][d], acc);
             }
         }
@@ -265,7 +275,7 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
         float dot = 0.f;
         for (int j = lane; j < T; j += 32) {
             float dp = row[j];
-            if (a.seed != 0) dp = attn_keep(a.seed, base + j, a.drop_p) ? dp * inv_keep : 0.f;
+            if (seed != 0) dp = attn_keep(seed, base + j, a.drop_p) ? dp * inv_keep : 0.f;
             row[j] = dp;
             dot = fmaf(dp, a.probs[base + j], dot);
         }
@@ -299,6 +309,7 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
 __global__ void __launch_bounds__(kAThreads)
 rpr_attn_bwd_kv_kernel(const AttnArgs a)
 {
+    const uint64_t seed = attn_seed(a);
     __shared__ float Qs[kAQ][kAD + 1], Ds[kAQ][kAD + 1];
     __shared__ float Pt[kAQ][kAQ + 1], St[kAQ][kAQ + 1];     // [i][j]
     const int tid = threadIdx.x;
@@ -320,7 +331,7 @@ rpr_attn_bwd_kv_kernel(const AttnArgs a)
             if (gi < T && gj < T) {
                 const size_t idx = ((size_t)(b * a.H + h) * T + gi) * T + gj;
                 pd = a.probs[idx];
-                if (a.seed != 0) pd = attn_keep(a.seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
+                if (seed != 0) pd = attn_keep(seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
                 ds = a.ds[idx];
             }
             Pt[i][jj] = pd;
@@ -367,6 +378,7 @@ static AttnArgs to_args(const glow_attn_call *c)
     a.scale = 1.f / sqrtf((float)c->head_dim);
     a.drop_p = c->dropout;
     a.seed = c->dropout > 0.f ? c->seed : 0;
+    a.step_dev = a.seed != 0 ? c->step_dev : nullptr;
     return a;
 }
 

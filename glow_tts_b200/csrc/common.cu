@@ -53,7 +53,7 @@ ProfScope::~ProfScope()
 
 extern "C" {
 
-int glow_abi_version(void) { return 1; }
+int glow_abi_version(void) { return 2; }
 
 const char *glow_last_error(void) { return glow::err_buf(); }
 

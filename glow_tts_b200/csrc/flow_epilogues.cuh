@@ -137,6 +137,7 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x)
 }
 struct DropCfg {
     uint64_t seed;      // 0 -> disabled
+    const uint64_t *step_dev;   // optional device step counter mixed into seed (CUDA-graph replays), or null
     uint64_t base;      // (block * layers + layer) * rows_pad
     float p, inv_keep;  // p, 1/(1-p) (inv_keep is re-derived from the 16-bit threshold on the device)
     // keep bits of packed columns (n, n+1), n even: bit 0 -> column n, bit 1 -> column n+1
@@ -144,7 +145,9 @@ struct DropCfg {
     __device__ __forceinline__ float scale() const { return 65536.f / (65536.f - (float)thresh()); }
     __device__ __forceinline__ uint32_t keep2(int row, int n) const
     {
-        const uint32_t s32 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
+        uint64_t sd = seed;
+        if (step_dev != nullptr) sd ^= __ldg(step_dev) * 0xD6E8FEB86659FD93ull;
+        const uint32_t s32 = (uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B1u);
         const uint32_t idx = ((uint32_t)base + (uint32_t)row) * (uint32_t)(kG / 2) + (uint32_t)(n >> 1);
         const uint32_t h = hash32(idx * 0x9E3779B1u + s32);
         const uint32_t t = thresh();

@@ -66,6 +66,7 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
     c.bw_act = (ActT *)call->bw_act;
     c.spk = call->spk;
     c.seed = call->seed;
+    c.step_dev = call->step_dev;
     c.training = call->training != 0;
     c.st = (cudaStream_t)call->stream;
     return c;

@@ -61,6 +61,7 @@ struct FlowCtx {
     ActT *bw_act;
     const float *spk;                // [B, spk_dim] or null
     uint64_t seed;                   // 0: no dropout (eval)
+    const uint64_t *step_dev;        // optional device step counter mixed into seed
     bool training;                   // keep per-block activations
     cudaStream_t st;
 };

@@ -37,6 +37,7 @@ inline DropCfg drop_cfg(const FlowCtx<ActT> &c, int k, int i)
 {
     DropCfg d;
     d.seed = (c.cfg.dropout > 0.f) ? c.seed : 0;
+    d.step_dev = d.seed != 0 ? c.step_dev : nullptr;
     d.base = ((uint64_t)k * kLayers + i) * (uint64_t)c.rows.rows_pad;
     d.p = c.cfg.dropout;
     d.inv_keep = 1.f / (1.f - c.cfg.dropout);

@@ -41,8 +41,14 @@ struct RadamArgs {
 
 __global__ void __launch_bounds__(256)
 radam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, size_t n,
-             RadamArgs a, const float *__restrict__ sqnorm, float *__restrict__ norm_out)
+             RadamArgs a, const float *__restrict__ hyper_dev, const float *__restrict__ sqnorm,
+             float *__restrict__ norm_out)
 {
+    if (hyper_dev != nullptr) {          // CUDA-graph mode: the schedule lives in device memory
+        a.lr = hyper_dev[0]; a.beta1 = hyper_dev[1]; a.beta2 = hyper_dev[2]; a.eps = hyper_dev[3];
+        a.weight_decay = hyper_dev[4]; a.step_size = hyper_dev[5]; a.rectified = hyper_dev[6] != 0.f;
+        a.max_norm = hyper_dev[7]; a.grad_scale = hyper_dev[8];
+    }
     float coef = a.grad_scale;
     if (sqnorm != nullptr) {
         const float total = sqrtf(*sqnorm) * a.grad_scale;
@@ -89,7 +95,22 @@ int glow_radam_step(float *params, float *grads, float *exp_avg, float *exp_avg_
     RadamArgs a{lr, beta1, beta2, eps, weight_decay, step_size, max_norm, grad_scale, rectified};
     const size_t want = (n + 255) / 256;
     const int grid = (int)(want < (size_t)(kNumSMs * 8) ? want : (size_t)(kNumSMs * 8));
-    radam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, a, sqnorm, norm_out);
+    radam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, a, nullptr, sqnorm,
+                                                         norm_out);
+    GLOW_CHECK_LAUNCH("radam_kernel");
+    return GLOW_OK;
+}
+
+int glow_radam_step_dev(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n,
+                        const float *hyper_dev, const float *sqnorm, float *norm_out, glow_stream_t stream)
+{
+    GLOW_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper_dev, GLOW_ERR_INVALID, "radam_step_dev: null pointer");
+    if (n == 0) return GLOW_OK;
+    RadamArgs a{};
+    const size_t want = (n + 255) / 256;
+    const int grid = (int)(want < (size_t)(kNumSMs * 8) ? want : (size_t)(kNumSMs * 8));
+    radam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, a, hyper_dev, sqnorm,
+                                                         norm_out);
     GLOW_CHECK_LAUNCH("radam_kernel");
     return GLOW_OK;
 }

@@ -125,6 +125,7 @@ class FlowPlan:
         c.cfg = self.cfg
         c.precision, c.batch, c.t_max, c.rows_pad = tag, rm.batch, int(t_max), rm.rows_pad
         c.training, c.seed = int(training), int(seed) & 0xFFFFFFFFFFFFFFFF
+        c.step_dev = _lib.step_counter_ptr(device) if seed else None
         c.row_utt, c.row_t = rm.row_utt.data_ptr(), rm.row_t.data_ptr()
         c.utt_off, c.utt_len = rm.utt_off.data_ptr(), rm.utt_len.data_ptr()
         c.wpack = wp.data_ptr()

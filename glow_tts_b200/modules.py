@@ -298,7 +298,7 @@ class Decoder(torch.nn.Module):
         rm = _flow.row_map(sq_len, x.device)
         xin = x[:, :, :t2]
         out_mask = (torch.arange(t2, device=x.device)[None, None, :] <
-                    (2 * torch.as_tensor(sq_len, device=x.device))[:, None, None]).to(x.dtype)
+                    (2 * _lib.device_ints(sq_len, torch.int64, x.device))[:, None, None]).to(x.dtype)
         self.flat_params()
         if reverse:
             with torch.no_grad():
@@ -545,7 +545,7 @@ class GlowTTS(torch.nn.Module):
     @staticmethod
     def _masks_from_host(lens, device):
         n = max(lens)
-        t = torch.as_tensor(lens, device=device)
+        t = _lib.device_ints(lens, torch.int64, device)
         return (torch.arange(n, device=device)[None, :] < t[:, None]).unsqueeze(1).float()
 
     def forward(self, tokens, token_lengths, mels, mel_lengths, speakers=None, mels_for_ge2e=None, pitches=None,
@@ -559,8 +559,8 @@ class GlowTTS(torch.nn.Module):
         spk = d["LUT"](speakers) if "LUT" in d else None
         token_masks = self._masks_from_host(tl, dev)[:, :, :tokens.shape[1]]
         mel_masks = self._masks_from_host(ml, dev)
-        t_len = torch.as_tensor(tl, dtype=torch.int32, device=dev)
-        m_len = torch.as_tensor(ml, dtype=torch.int32, device=dev)
+        t_len = _lib.device_ints(tl, torch.int32, dev)
+        m_len = _lib.device_ints(ml, torch.int32, dev)
 
         mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk, None,
                                                            lengths=t_len)
@@ -593,7 +593,7 @@ class GlowTTS(torch.nn.Module):
         spk = d["LUT"](speakers) if "LUT" in d else None
         tl = _host_lengths(lengths=token_lengths)
         token_masks = self._masks_from_host(tl, dev)
-        t_len = torch.as_tensor(tl, dtype=torch.int32, device=dev)
+        t_len = _lib.device_ints(tl, torch.int32, dev)
         mean, log_std, log_dur, mask = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk, None,
                                                     lengths=t_len)
         if not torch.is_tensor(length_scale):

@@ -31,6 +31,7 @@ class _AttnCoreFn(torch.autograd.Function):
         call.mask = mask_c.data_ptr() if mask_c is not None else None
         call.batch, call.heads, call.t, call.head_dim, call.window = b, heads, t, d, window
         call.dropout, call.seed = float(dropout), int(seed)
+        call.step_dev = _lib.step_counter_ptr(dev) if seed else None
         needs_grad = any(ctx.needs_input_grad[:5])
         out = torch.empty_like(q)
         probs = torch.empty((b, heads, t, t), dtype=torch.float32, device=dev) if needs_grad else None

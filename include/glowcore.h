@@ -141,6 +141,9 @@ typedef struct {
     int       rows_pad;
     int       training;      /* 1: keep every block's activations for glow_flow_backward */
     uint64_t  seed;          /* dropout stream of this step; 0 = no dropout (eval) */
+    const uint64_t *step_dev; /* optional DEVICE step counter mixed into `seed` inside the kernels: a call
+                                captured in a CUDA graph draws fresh dropout masks on every replay
+                                (the reference draws from torch's RNG stream, Modules.py:862). NULL: unused */
     const int32_t *row_utt, *row_t, *utt_off, *utt_len;
     const float *wpack;      /* glow_flow_prepare output (glow_flow_wpack_floats floats) */
     const void  *wpack_tc;   /* bf16 slab images (glow_flow_wpack_tc_elems), bf16 mode only */
@@ -193,6 +196,7 @@ typedef struct {
     int   batch, heads, t, head_dim, window;
     float dropout;              /* on the probabilities, only when seed != 0 */
     uint64_t seed;
+    const uint64_t *step_dev;   /* optional device step counter mixed into `seed` (CUDA-graph replays), or NULL */
     glow_stream_t stream;
 } glow_attn_call;
 
@@ -221,6 +225,13 @@ int glow_radam_step(float *params, float *grads, float *exp_avg, float *exp_avg_
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     float step_size, int rectified, float max_norm, float grad_scale,
                     const float *sqnorm, float *norm_out, glow_stream_t stream);
+/* Same update with the nine scalars read from DEVICE memory, hyper_dev = {lr, beta1, beta2, eps,
+ * weight_decay, step_size, rectified (0/1), max_norm, grad_scale}: the launch carries no per-step
+ * value, so it can be captured once in a CUDA graph and replayed while the host advances the
+ * schedule (Radam.py:61-76, Noam_Scheduler.py:17-29) by rewriting that buffer. */
+int glow_radam_step_dev(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n,
+                        const float *hyper_dev, const float *sqnorm, float *norm_out,
+                        glow_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * Hardware self-test of the tcgen05 / TMEM / bulk-copy layer (csrc/umma.cuh):

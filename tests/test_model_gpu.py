@@ -93,6 +93,51 @@ def test_three_train_steps_match_reference(case):
     assert abs(float(flat.double().norm()) - g["train_param_digest"][0]) < 1e-4 * g["train_param_digest"][0]
 
 
+def test_graphed_train_steps_match_reference(case):
+    """The same three steps with steps 2 and 3 replayed from the captured CUDA graph."""
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep, GraphedTrainStep
+    name = [k for k, v in CASES.items() if v[0] == case[4]][0]
+    model, sd, g, batch, mode = load_case(name, "fp32")
+    model.eval()
+    hp = load_hparams(Mode=mode, Precision="fp32")
+    step = TrainStep(model, hp, torch.device("cuda:0"))
+    graphed = GraphedTrainStep(step, batch, warmup=1)         # step 1 runs eagerly as the warm-up
+    lasts = [dict((k, float(v)) for k, v in graphed.warmup_last.items())]
+    for i in (1, 2):
+        graphed.run(batch if i == 1 else None)                 # once through load(), once on resident inputs
+        torch.cuda.synchronize()
+        lasts.append(dict((k, float(v)) for k, v in graphed.last.items()))
+    for i, got in enumerate(lasts):
+        want = g["train_losses"][i]
+        assert abs(got["mle"] - want[0]) < 2e-3 * abs(want[0]), i
+        assert abs(got["mse"] - want[1]) < 2e-3 * abs(want[1]), i
+        assert abs(got["grad_norm"] - want[2]) < 5e-3 * abs(want[2]), i
+    flat = torch.cat([p.detach().flatten() for p in model.parameters()]).cpu()
+    assert abs(float(flat.double().norm()) - g["train_param_digest"][0]) < 1e-4 * g["train_param_digest"][0]
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    """Two replays of one captured training step must not reuse the dropout masks: the kernels mix the
+    device step counter into their seeds (glow_flow_call.step_dev / glow_attn_call.step_dev)."""
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep, GraphedTrainStep
+    model, sd, g, batch, mode = load_case("vanilla_small", "fp32")
+    model.train()
+    hp = load_hparams(Mode=mode, Precision="fp32")
+    step = TrainStep(model, hp, torch.device("cuda:0"))
+    step.opt.lr0 = 0.0                                         # freeze the weights: only the masks can change the loss
+    step.opt.wd = 0.0
+    graphed = GraphedTrainStep(step, batch, warmup=1)
+    losses = []
+    for _ in range(3):
+        graphed.run()
+        torch.cuda.synchronize()
+        losses.append(float(graphed.last["mle"]))
+    assert len(set(losses)) == 3, losses
+    assert max(losses) - min(losses) < 0.2 * abs(losses[0]), losses
+
+
 def test_state_dict_roundtrip_and_cpu_is_refused():
     from glow_tts_b200 import _lib
     model, sd, g, batch, mode = load_case("vanilla_small", "fp32")

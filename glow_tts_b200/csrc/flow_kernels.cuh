@@ -78,6 +78,14 @@ int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, fl
 int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
                        float *dmel, float *dspk, bool tc);
 
+// Side stream for the weight-gradient GEMMs (flow_wgrad.cu): one per device, with fork / done
+// events per block parity.  Works under CUDA-graph capture (the event waits pull it into the capture).
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork[2], done[2];
+};
+int side_stream(SideStream **out);
+
 // cuBLAS weight-gradient GEMMs (flow_wgrad.cu), row-major:
 //   C[b][K][N] (ldc) = beta*C + A_b[rows,K]^T * D[rows,N],  A_b = A + b*strideA, C_b = C + b*strideC
 int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,

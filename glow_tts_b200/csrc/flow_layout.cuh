@@ -145,7 +145,11 @@ struct WorkLayout {
     size_t dz, dy;                  // fp32 [rows][160] x2
     size_t dspkb;                   // fp32 [layers][B][384]
     size_t bwd_f32_total;
-    size_t douts, dout, dh[2], dins, dpre;   // ActT: [rows][160], [rows][192], 2x[rows][192], [rows][384] x2
+    // ActT, two SETS (block parity): a block's weight-gradient GEMMs run on a side stream while the
+    // main stream already computes the next block's data gradients, so the gradients they read must
+    // outlive the block: douts [rows][160], dout [rows][192], dh[layer] [rows][192] (d h_i),
+    // dpre[layer] [rows][384] (d gate pre-activation before dropout); dins [rows][384] is main-stream only.
+    size_t douts[2], dout[2], dh[2][kLayers], dpre[2][kLayers], dins;
     size_t bwd_act_total;
 };
 
@@ -174,9 +178,11 @@ inline WorkLayout make_work_layout(int blocks, size_t rows, int batch, bool trai
     w.dspkb = take((size_t)kLayers * batch * kG);
     w.bwd_f32_total = training ? o : 0;
     o = 0;
-    w.douts = take(rows * kC); w.dout = take(rows * kH);
-    w.dh[0] = take(rows * kH); w.dh[1] = take(rows * kH);
-    w.dins = take(rows * kG); w.dpre = take(rows * kG);
+    for (int s = 0; s < 2; ++s) {
+        w.douts[s] = take(rows * kC); w.dout[s] = take(rows * kH);
+        for (int i = 0; i < kLayers; ++i) { w.dh[s][i] = take(rows * kH); w.dpre[s][i] = take(rows * kG); }
+    }
+    w.dins = take(rows * kG);
     w.bwd_act_total = training ? o : 0;
     return w;
 }

@@ -208,6 +208,9 @@ int flow_reverse_impl(const FlowCtx<ActT> &c, const float *z, int T, float *mel,
 }
 
 // ------------------------------------------------------------- backward ------
+// Data gradients run block by block on the caller's stream; the weight / bias gradients of a block
+// (13 reductions over the packed row axis + 13 column sums) are forked to a side stream once the
+// block's chain is done, so they overlap the next block's latency-bound dgrad kernels.
 template <typename ActT, bool FAST, class Ops>
 int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
                        float *dmel, float *dspk)
@@ -215,46 +218,33 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
     const int R = c.rows.rows_pad, B = c.rows.batch;
     constexpr bool kBf16 = sizeof(ActT) == 2;
     float *DZ = c.bw_f32 + c.wl.dz, *DY = c.bw_f32 + c.wl.dy;
-    ActT *DOUTS = c.bw_act + c.wl.douts, *DOUT = c.bw_act + c.wl.dout;
-    ActT *DHb[2] = {c.bw_act + c.wl.dh[0], c.bw_act + c.wl.dh[1]};
     ActT *DINS = c.bw_act + c.wl.dins;
-    const bool drop_on = c.cfg.dropout > 0.f && c.seed != 0;
-    ActT *DPRE = drop_on ? c.bw_act + c.wl.dpre : DINS;
+    SideStream *ss = nullptr;
+    GLOW_TRY(side_stream(&ss));
+    cudaStream_t side = ss->stream;
     GLOW_CHECK_CUDA(cudaMemsetAsync(dwpack, 0, sizeof(float) * c.bp.total * c.cfg.blocks, c.st));
     pack_rows_kernel<float><<<R / 32, 256, 0, c.st>>>(dz, T, c.rows, DZ, (float *)nullptr, nullptr, nullptr, nullptr);
     GLOW_CHECK_LAUNCH("pack_rows_kernel");
     const int G2 = kGuard;                       // wgrad GEMMs skip the leading/trailing guard rows
     const int Rw = R - 2 * G2;
     for (int k = c.cfg.blocks - 1; k >= 0; --k) {
+        const int set = k & 1;
+        if (k + 2 < c.cfg.blocks) GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[set], 0));   // set is free again
         Bufs<ActT> b = block_bufs(c, k);
         float *dwp = dwpack + (size_t)k * c.bp.total;
+        ActT *DOUTS = c.bw_act + c.wl.douts[set], *DOUT = c.bw_act + c.wl.dout[set];
+        ActT *DH[kLayers], *DPRE[kLayers];
+        for (int i = 0; i < kLayers; ++i) { DH[i] = c.bw_act + c.wl.dh[set][i]; DPRE[i] = c.bw_act + c.wl.dpre[set][i]; }
+        // ---- data gradients (main stream)
         const size_t n_el = (size_t)R * kCh;
         coupling_bwd_kernel<ActT><<<(unsigned)((n_el + 255) / 256), 256, 0, c.st>>>(DZ, b.Y, b.OUTS, dlogdet,
                                                                                    c.rows.row_utt, R, DOUTS, DY);
         GLOW_CHECK_LAUNCH("coupling_bwd_kernel");
         GLOW_TRY(Ops::b_end(c, k, DOUTS, DOUT));
-        // dW_end[192][160] = OUT^T DOUTS ; db_end
-        GLOW_TRY(wgrad_gemm(c.st, kBf16, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f));
-        colsum_kernel<ActT><<<dim3(kC / 32, 32), 256, 0, c.st>>>(DOUTS, kC, R, kC, dwp + c.bp.end_b);
-        GLOW_CHECK_LAUNCH("colsum_kernel");
-        const ActT *DHnext = nullptr;
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
-            const int rs_n = last ? kH : kG;
-            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, DINS, DPRE));
-            // dW_rs[192][rs_n]: res columns from d(h_{i+1}), skip columns from d(out)
-            if (!last) {
-                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DHnext, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
-                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f));
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DHnext, kH, R, kH, dwp + c.bp.rs_b[i]);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i] + kH);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
-            } else {
-                GLOW_TRY(wgrad_gemm(c.st, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i]);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
-            }
+            const ActT *DHnext = last ? nullptr : DH[i + 1];
+            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, DINS, DPRE[i]));
             if (c.spk != nullptr) {
                 float *dspkb = c.bw_f32 + c.wl.dspkb;
                 seg_colsum_kernel<ActT><<<dim3(kG / 128, B), 128, 0, c.st>>>(DINS, kG, kG, c.rows.utt_off,
@@ -265,28 +255,55 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
                                                                dwp + c.bp.spk_w[i], dwp + c.bp.spk_b[i], dspk);
                 GLOW_CHECK_LAUNCH("spk_bwd_kernel");
             }
-            ActT *DH = DHb[i & 1];
-            GLOW_TRY(Ops::b_in(c, k, i, DPRE, last ? nullptr : DHnext, DH));
-            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
-            GLOW_TRY(wgrad_gemm(c.st, kBf16, b.H[i], kH, DPRE + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
-                                kTaps, kH, (long long)kH * kG, 0.f));
-            colsum_kernel<ActT><<<dim3(kG / 32, 32), 256, 0, c.st>>>(DPRE, kG, R, kG, dwp + c.bp.in_b[i]);
-            GLOW_CHECK_LAUNCH("colsum_kernel");
-            DHnext = DH;
+            GLOW_TRY(Ops::b_in(c, k, i, DPRE[i], DHnext, DH[i]));
         }
-        GLOW_TRY(Ops::b_start(c, k, DHnext, DY));
-        if (kBf16) {
-            GLOW_TRY(wgrad_gemm(c.st, true, b.YA, kCh, DHnext, kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
-        } else {
-            GLOW_TRY(wgrad_gemm(c.st, false, b.Y, kC, DHnext, kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
-        }
-        colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, c.st>>>(DHnext, kH, R, kH, dwp + c.bp.start_b);
+        GLOW_TRY(Ops::b_start(c, k, DH[0], DY));
+        // ---- weight / bias gradients of this block (side stream)
+        GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
+        GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
+        // dW_end[192][160] = OUT^T DOUTS ; db_end
+        GLOW_TRY(wgrad_gemm(side, kBf16, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f));
+        colsum_kernel<ActT><<<dim3(kC / 32, 32), 256, 0, side>>>(DOUTS, kC, R, kC, dwp + c.bp.end_b);
         GLOW_CHECK_LAUNCH("colsum_kernel");
+        for (int i = kLayers - 1; i >= 0; --i) {
+            const bool last = i == kLayers - 1;
+            const int rs_n = last ? kH : kG;
+            // dW_rs[192][rs_n]: res columns from d(h_{i+1}), skip columns from d(out)
+            if (!last) {
+                GLOW_TRY(wgrad_gemm(side, kBf16, b.ACTS[i], kH, DH[i + 1], kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
+                GLOW_TRY(wgrad_gemm(side, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f));
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DH[i + 1], kH, R, kH, dwp + c.bp.rs_b[i]);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i] + kH);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+            } else {
+                GLOW_TRY(wgrad_gemm(side, kBf16, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
+                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i]);
+                GLOW_CHECK_LAUNCH("colsum_kernel");
+            }
+            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
+            GLOW_TRY(wgrad_gemm(side, kBf16, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
+                                kTaps, kH, (long long)kH * kG, 0.f));
+            colsum_kernel<ActT><<<dim3(kG / 32, 32), 256, 0, side>>>(DPRE[i], kG, R, kG, dwp + c.bp.in_b[i]);
+            GLOW_CHECK_LAUNCH("colsum_kernel");
+        }
+        if (kBf16) {
+            GLOW_TRY(wgrad_gemm(side, true, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
+        } else {
+            GLOW_TRY(wgrad_gemm(side, false, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
+        }
+        colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DH[0], kH, R, kH, dwp + c.bp.start_b);
+        GLOW_CHECK_LAUNCH("colsum_kernel");
+        GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
+        // ---- back on the main stream: 4x4 mix + ActNorm backward -> dz of the previous block
         const bool need_dz = k > 0 || dmel != nullptr;
         mix_bwd_kernel<<<R / 32, 256, 0, c.st>>>(DY, b.Y, c.rows.row_utt, R, c.wpack + (size_t)k * c.bp.total, c.bp, dwp,
                                                 need_dz ? DZ : nullptr);
         GLOW_CHECK_LAUNCH("mix_bwd_kernel");
     }
+    // join: every forked block must be back before the caller reads dwpack (and before a capture ends)
+    GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[0], 0));
+    if (c.cfg.blocks > 1) GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[1], 0));
     if (dmel != nullptr) {
         unpack_rows_kernel<<<dim3((T + 63) / 64, B), 256, 0, c.st>>>(DZ, c.rows.utt_off, c.rows.utt_len, T, dmel, 0.f);
         GLOW_CHECK_LAUNCH("unpack_rows_kernel");

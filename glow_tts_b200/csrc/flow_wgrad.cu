@@ -27,6 +27,28 @@ static int get_handle(cublasHandle_t *out)
     return GLOW_OK;
 }
 
+static SideStream g_side[16];
+static bool g_side_init[16] = {false};
+
+int side_stream(SideStream **out)
+{
+    int dev = 0;
+    GLOW_CHECK_CUDA(cudaGetDevice(&dev));
+    GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
+    std::lock_guard<std::mutex> lock(g_handle_mu);
+    if (!g_side_init[dev]) {
+        SideStream &s = g_side[dev];
+        GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
+            GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
+        }
+        g_side_init[dev] = true;
+    }
+    *out = &g_side[dev];
+    return GLOW_OK;
+}
+
 int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
                float *C, int ldc, int batch, long long strideA, long long strideC, float beta)
 {

@@ -37,7 +37,12 @@ class AttnCall(ctypes.Structure):            # glow_attn_call
                 ("dropout", _F), ("seed", _U64), ("step_dev", _P), ("stream", _P)]
 
 
+class RowsConvCall(ctypes.Structure):        # glow_rows_conv_call
+    _fields_ = [("cin", _I), ("cout", _I), ("taps", _I), ("rows_pad", _I), ("row_utt", _P), ("stream", _P)]
+
+
 _PCFG, _PCALL, _PATTN = ctypes.POINTER(FlowConfig), ctypes.POINTER(FlowCall), ctypes.POINTER(AttnCall)
+_PROWS = ctypes.POINTER(RowsConvCall)
 
 # name -> (restype, argtypes); kept in step with include/glowcore.h
 # (tests/test_abi.py parses the header and checks every declared symbol is here
@@ -62,6 +67,11 @@ SIGNATURES = {
     "glow_flow_param_grads": (_I, [_PCFG, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "glow_rpr_attention_forward": (_I, [_PATTN, _P, _P, _P]),
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "glow_rows_conv_slab_elems": (_Z, [_I, _I, _I]),
+    "glow_rows_conv_pack": (_I, [_PROWS, _P, _P, _P]),
+    "glow_rows_conv_forward": (_I, [_PROWS, _P, _P, _P, _P]),
+    "glow_rows_conv_backward_data": (_I, [_PROWS, _P, _P, _P]),
+    "glow_rows_conv_backward_weight": (_I, [_PROWS, _P, _P, _P, _P]),
     "glow_sqnorm": (_I, [_P, _Z, _P, _P]),
     "glow_radam_step": (_I, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _F, _F, _P, _P, _P]),
     "glow_radam_step_dev": (_I, [_P, _P, _P, _P, _Z, _P, _P, _P, _P]),

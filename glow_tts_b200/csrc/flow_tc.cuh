@@ -34,9 +34,12 @@
 
 namespace glow {
 
-struct TcA {                         // A operand: NP panels of KP bf16 columns each
-    const __nv_bfloat16 *p[2];       // panel p starts at p[p] (same tensor + KP columns, or a second tensor)
+struct TcA {                         // A operand: NP panels of KP columns each
+    const void *p[4];                // panel p starts at p[p] (same tensor + KP columns, or another tensor)
 };
+// AMODE 0: A is bf16.  AMODE 1: A is fp32, converted to bf16 while it is staged, and rows whose
+// row_utt is < 0 (guard / tail rows) are staged as zeros -- the reference's `x * mask` in front of
+// every encoder conv (Modules.py:554,567,570) folded into the load.
 
 constexpr int kTcRows = 128 + 2 * kGuard;   // staged rows per tile
 constexpr int kTcPitch = 133 * 16;          // slab pitch in bytes: 133 rows -> conflict-free 16 B staging stores
@@ -74,10 +77,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32])      /
 //   KS: K per weight stage.
 template <int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS>
 struct TcCfg {
+    static constexpr int kCenter = (TAPS - 1) / 2;
     static_assert(N % BN == 0 && BN % 16 == 0 && BN <= 256, "BN");
     static_assert(KP % 16 == 0 && KP <= 192 && KP % KS == 0 && KS % 16 == 0, "KP / KS");
-    static_assert(NP == 1 || NP == 2, "NP");
-    static_assert(TAPS == 1 || TAPS == kTaps, "TAPS");
+    static_assert(NP >= 1 && NP <= 4, "NP");
+    static_assert(TAPS == 1 || TAPS == 3 || TAPS == 5, "TAPS");
+    static_assert((TAPS - 1) / 2 <= kGuard, "taps reach beyond the staged guard rows");
     static_assert(LD % 8 == 0 && LD >= KP, "LD");
     static constexpr int kSlices = N / BN;
     static constexpr int kKpch = KP / 8;                       // 16 B chunks per panel row
@@ -97,7 +102,7 @@ struct TcCfg {
                                                       : (2 * BN <= 256) ? 256u : 512u;
 };
 
-template <class Cfg, int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS, class Epi>
+template <class Cfg, int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS, int AMODE, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int32_t *__restrict__ row_utt,
                 const int n_items, const int rows_pad, const Epi epi, long long *__restrict__ dbg_all)
@@ -145,29 +150,60 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
                 if (pc >= 2) mbar_wait(&a_empty[buf], ((pc >> 1) - 1u) & 1u);
                 if (active) {
                     const uint32_t dst = smem_u32(smem) + buf * Cfg::kPanelBytes + (uint32_t)c * kTcPitch + (uint32_t)r0 * 16u;
-                    const __nv_bfloat16 *src = a.p[p] + c * 8;
                     // register-staged: LDG.128 batches (coalesced along the row) -> STS.128 into the slabs.
                     // (LDGSTS with per-lane scattered shared destinations and 16 B-row TMA boxes both run
                     // at about one 16 B row per cycle: profiles/ubench_r01.md.)  Rows outside [0, rows_pad)
                     // (first / last tile) read a zero guard row instead: rows 0-1 and the last rows of every
                     // packed buffer are guards (flow_layout.cuh).
-                    constexpr int kBatch = 14;
+                    if constexpr (AMODE == 0) {
+                        const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(a.p[p]) + c * 8;
+                        constexpr int kBatch = 14;
 #pragma unroll
-                    for (int k0 = 0; k0 < Cfg::kLoadIters; k0 += kBatch) {
-                        uint4 t[kBatch];
+                        for (int k0 = 0; k0 < Cfg::kLoadIters; k0 += kBatch) {
+                            uint4 t[kBatch];
 #pragma unroll
-                        for (int k = 0; k < kBatch; ++k) {
-                            const int r = r0 + (k0 + k) * Cfg::kRowsStep;
-                            if (k0 + k < Cfg::kLoadIters && r < kTcRows) {
-                                int row = row0 + r;
-                                if (!interior) row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
-                                t[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * LD));
+                            for (int k = 0; k < kBatch; ++k) {
+                                const int r = r0 + (k0 + k) * Cfg::kRowsStep;
+                                if (k0 + k < Cfg::kLoadIters && r < kTcRows) {
+                                    int row = row0 + r;
+                                    if (!interior) row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
+                                    t[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * LD));
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int k = 0; k < kBatch; ++k)
-                            if (k0 + k < Cfg::kLoadIters && r0 + (k0 + k) * Cfg::kRowsStep < kTcRows)
-                                st_shared16(dst + (uint32_t)((k0 + k) * Cfg::kRowsStep * 16), t[k]);
+                            for (int k = 0; k < kBatch; ++k)
+                                if (k0 + k < Cfg::kLoadIters && r0 + (k0 + k) * Cfg::kRowsStep < kTcRows)
+                                    st_shared16(dst + (uint32_t)((k0 + k) * Cfg::kRowsStep * 16), t[k]);
+                        }
+                    } else {
+                        const float *src = reinterpret_cast<const float *>(a.p[p]) + c * 8;
+                        constexpr int kBatch = 7;
+#pragma unroll
+                        for (int k0 = 0; k0 < Cfg::kLoadIters; k0 += kBatch) {
+                            float4 t0[kBatch], t1[kBatch];
+                            int u[kBatch];
+#pragma unroll
+                            for (int k = 0; k < kBatch; ++k) {
+                                const int r = r0 + (k0 + k) * Cfg::kRowsStep;
+                                if (k0 + k < Cfg::kLoadIters && r < kTcRows) {
+                                    int row = row0 + r;
+                                    row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
+                                    const float4 *g = reinterpret_cast<const float4 *>(src + (size_t)row * LD);
+                                    t0[k] = __ldg(g);
+                                    t1[k] = __ldg(g + 1);
+                                    u[k] = __ldg(row_utt + row);
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < kBatch; ++k)
+                                if (k0 + k < Cfg::kLoadIters && r0 + (k0 + k) * Cfg::kRowsStep < kTcRows) {
+                                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                                    if (u[k] >= 0)
+                                        v = make_uint4(pack_bf16x2(t0[k].x, t0[k].y), pack_bf16x2(t0[k].z, t0[k].w),
+                                                       pack_bf16x2(t1[k].x, t1[k].y), pack_bf16x2(t1[k].z, t1[k].w));
+                                    st_shared16(dst + (uint32_t)((k0 + k) * Cfg::kRowsStep * 16), v);
+                                }
+                        }
                     }
                 }
                 fence_proxy_async();                                   // generic-proxy writes -> tcgen05.mma reads
@@ -213,7 +249,7 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
                     if (dbg && it < 2 && p == 0) dbg[8 + it * 8] = clock64();
                     // descriptors advance in 16 B units: one row per tap step, 2 slabs per 16-wide K step
                     uint64_t a_tap = smem_desc(a_base + buf * Cfg::kPanelBytes +
-                                                   (uint32_t)((TAPS == 1) ? kGuard : kGuard - DIR * ((kTaps - 1) / 2)) * 16u,
+                                                   (uint32_t)(kGuard - DIR * Cfg::kCenter) * 16u,
                                                kTcPitch, 128);
 #pragma unroll 1
                     for (int tap = 0; tap < TAPS; ++tap, a_tap += (uint64_t)(int64_t)DIR) {
@@ -311,13 +347,13 @@ inline void tc_debug_print(const char *name, int grid, int n_items, int stages, 
     }
 }
 
-template <int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS, class Epi>
+template <int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS, int AMODE, class Epi>
 int gemm_tc3(const TcA &a, const __nv_bfloat16 *Wslab, const int32_t *row_utt, int rows_pad, const Epi &epi,
              cudaStream_t st, const char *name)
 {
     using Cfg = TcCfg<N, BN, KP, NP, LD, TAPS, DIR, KS>;
     GLOW_REQUIRE(rows_pad % 128 == 0, GLOW_ERR_INVALID, "%s: tensor-core GEMM rows=%d", name, rows_pad);
-    auto kern = tc_gemm3_kernel<Cfg, N, BN, KP, NP, LD, TAPS, DIR, KS, Epi>;
+    auto kern = tc_gemm3_kernel<Cfg, N, BN, KP, NP, LD, TAPS, DIR, KS, AMODE, Epi>;
     static bool attr_set = false;                  // per template instantiation
     if (!attr_set) {
         GLOW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -356,12 +392,12 @@ struct TcOps {
     using Ctx = FlowCtx<ActT>;
     static const float *wp(const Ctx &c, int k) { return c.wpack + (size_t)k * c.bp.total; }
     static const ActT *ws(const Ctx &c, int k) { return c.wpack_tc + (size_t)k * c.bt.total; }
-    static TcA one(const ActT *p) { return TcA{{p, p}}; }
+    static TcA one(const ActT *p) { return TcA{{p, p, p, p}}; }
 
     static int start(const Ctx &c, int k, const Bufs<ActT> &b)
     {
         EpiStart<ActT> e{wp(c, k) + c.bp.start_b, b.H[0], c.rows.row_utt};
-        return gemm_tc3<kH, kBnH, kCh, 1, kCh, 1, 0, kCh>(one(b.YA), ws(c, k) + c.bt.start_w, c.rows.row_utt,
+        return gemm_tc3<kH, kBnH, kCh, 1, kCh, 1, 0, kCh, 0>(one(b.YA), ws(c, k) + c.bt.start_w, c.rows.row_utt,
                                                           c.rows.rows_pad, e, c.st, "start");
     }
     static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
@@ -369,27 +405,27 @@ struct TcOps {
         const bool last = i == kLayers - 1;
         EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
                                drop_cfg(c, k, i)};
-        int rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
+        int rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs, 0>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
                                                                     c.rows.rows_pad, eg, c.st, "in_gate");
         if (rc) return rc;
         EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
                             c.rows.row_utt, i == 0, last};
         if (last)
-            return gemm_tc3<kH, kBnH, kH, 1, kH, 1, 0, kTcKs>(one(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+            return gemm_tc3<kH, kBnH, kH, 1, kH, 1, 0, kTcKs, 0>(one(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
                                                               c.rows.rows_pad, er, c.st, "res_skip");
-        return gemm_tc3<kG, kBnGate, kH, 1, kH, 1, 0, kTcKs>(one(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+        return gemm_tc3<kG, kBnGate, kH, 1, kH, 1, 0, kTcKs, 0>(one(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
                                                              c.rows.rows_pad, er, c.st, "res_skip");
     }
     static int end(const Ctx &c, int k, const Bufs<ActT> &b, const EpiEnd<ActT, FAST> &e)
     {
-        return gemm_tc3<kC, kBnEnd, kH, 1, kH, 1, 0, kTcKs>(one(b.OUT), ws(c, k) + c.bt.end_w, c.rows.row_utt,
+        return gemm_tc3<kC, kBnEnd, kH, 1, kH, 1, 0, kTcKs, 0>(one(b.OUT), ws(c, k) + c.bt.end_w, c.rows.row_utt,
                                                             c.rows.rows_pad, e, c.st, "end");
     }
     // backward
     static int b_end(const Ctx &c, int k, const ActT *DOUTS, ActT *DOUT)
     {
         EpiBwdEnd<ActT> e{DOUT, c.rows.row_utt};
-        return gemm_tc3<kH, kBnH, kC, 1, kC, 1, 0, kC / 2>(one(DOUTS), ws(c, k) + c.bt.end_wt, c.rows.row_utt,
+        return gemm_tc3<kH, kBnH, kC, 1, kC, 1, 0, kC / 2, 0>(one(DOUTS), ws(c, k) + c.bt.end_wt, c.rows.row_utt,
                                                            c.rows.rows_pad, e, c.st, "b_end");
     }
     static int b_rs(const Ctx &c, int k, int i, const Bufs<ActT> &b, const ActT *DHnext, const ActT *DOUT,
@@ -397,23 +433,23 @@ struct TcOps {
     {
         EpiBwdGate<ActT> e{b.TS[i], DINS, DPRE, c.rows.row_utt, drop_cfg(c, k, i)};
         if (i == kLayers - 1)
-            return gemm_tc3<kH, kBnH, kH, 1, kH, 1, 0, kTcKs>(one(DOUT), ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt,
+            return gemm_tc3<kH, kBnH, kH, 1, kH, 1, 0, kTcKs, 0>(one(DOUT), ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt,
                                                               c.rows.rows_pad, e, c.st, "b_rs");
-        TcA a{{DHnext, DOUT}};                            // K-concatenated: d(res) | d(skip)
-        return gemm_tc3<kH, kBnH, kH, 2, kH, 1, 0, kTcKs>(a, ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt, c.rows.rows_pad, e,
+        TcA a{{DHnext, DOUT, nullptr, nullptr}};                            // K-concatenated: d(res) | d(skip)
+        return gemm_tc3<kH, kBnH, kH, 2, kH, 1, 0, kTcKs, 0>(a, ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt, c.rows.rows_pad, e,
                                                           c.st, "b_rs");
     }
     static int b_in(const Ctx &c, int k, int i, const ActT *DPRE, const ActT *DHnext, ActT *DH)
     {
-        TcA a{{DPRE, DPRE + kH}};
+        TcA a{{DPRE, DPRE + kH, nullptr, nullptr}};
         EpiBwdIn<ActT> e{DHnext, DH, c.rows.row_utt};
-        return gemm_tc3<kH, kBnH, kH, 2, kG, kTaps, -1, kTcKs>(a, ws(c, k) + c.bt.in_wt[i], c.rows.row_utt,
+        return gemm_tc3<kH, kBnH, kH, 2, kG, kTaps, -1, kTcKs, 0>(a, ws(c, k) + c.bt.in_wt[i], c.rows.row_utt,
                                                                c.rows.rows_pad, e, c.st, "b_in");
     }
     static int b_start(const Ctx &c, int k, const ActT *DH0, float *DY)
     {
         EpiBwdStart e{DY};
-        return gemm_tc3<kCh, kBnHalf, kH, 1, kH, 1, 0, kTcKs>(one(DH0), ws(c, k) + c.bt.start_wt, c.rows.row_utt,
+        return gemm_tc3<kCh, kBnHalf, kH, 1, kH, 1, 0, kTcKs, 0>(one(DH0), ws(c, k) + c.bt.start_wt, c.rows.row_utt,
                                                               c.rows.rows_pad, e, c.st, "b_start");
     }
 };

@@ -49,7 +49,7 @@ int side_stream(SideStream **out)
     return GLOW_OK;
 }
 
-int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
+int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
                float *C, int ldc, int batch, long long strideA, long long strideC, float beta)
 {
     cublasHandle_t h;
@@ -59,8 +59,10 @@ int wgrad_gemm(cudaStream_t st, bool bf16, const void *A, int lda, const void *D
     cublasStatus_t s = cublasSetStream(h, st);
     GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasSetStream failed: %d", (int)s);
     const float alpha = 1.f;
-    const cudaDataType_t in_t = bf16 ? CUDA_R_16BF : CUDA_R_32F;
-    const cublasComputeType_t comp = bf16 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_PEDANTIC;
+    // mode 0: fp32 operands, fp32 math (parity mode); 1: bf16 operands; 2: fp32 operands rounded to bf16 by cuBLAS
+    const cudaDataType_t in_t = mode == 1 ? CUDA_R_16BF : CUDA_R_32F;
+    const cublasComputeType_t comp = mode == 1 ? CUBLAS_COMPUTE_32F
+                                               : (mode == 2 ? CUBLAS_COMPUTE_32F_FAST_16BF : CUBLAS_COMPUTE_32F_PEDANTIC);
     if (batch <= 1) {
         s = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, K, rows, &alpha, D, in_t, ldd, A, in_t, lda, &beta, C,
                          CUDA_R_32F, ldc, comp, CUBLAS_GEMM_DEFAULT);

@@ -1,0 +1,154 @@
+// rows_conv.cu -- the text encoder's convolutions (Modules.py:461-573 CLRD / ANCRDCN convs,
+// RPR_MHA.py:59-66 Query/Key/Value/Projection, Modules.py:252 Project) over PACKED token rows,
+// on the tcgen05 GEMM of flow_tc.cuh.
+//
+//   y[row, :] = row_utt[row] >= 0 ? bias + sum_tap W[tap] x[row + tap - c, :] : 0
+//
+// x, y are fp32 [rows_pad, C] (the same packed row axis as the decoder: utterances separated by two
+// zero-valued guard rows, which are the convs' zero padding); rows with row_utt < 0 are READ as
+// zeros (the reference's `x * mask` in front of every conv) and WRITTEN as zeros.  Operands are
+// rounded to bf16 as they are staged, products accumulate in fp32 in TMEM.
+#include "flow_tc.cuh"
+
+namespace glow {
+
+// y = mask * (acc + bias)   (bias null: data-gradient GEMM)
+struct EpiRows {
+    const float *bias; float *out; int ldo;
+    template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
+    {
+        float b[NV], o[NV];
+        if (bias != nullptr) ld_vec<NV>(bias + n0, b);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) o[j] = utt >= 0 ? v[j] + (bias != nullptr ? b[j] : 0.f) : 0.f;
+        st_vec<NV>(out + (size_t)row * ldo + n0, o);
+    }
+};
+
+// column slice per item, by output width (token batches are small: prefer more, narrower items)
+constexpr int rows_bn(int n) { return n == 768 ? 128 : n == 192 ? 96 : n == 160 ? 80 : 0; }
+
+struct RowsShape { int cin, cout, taps; };
+static const RowsShape kRowsShapes[] = {{192, 192, 5}, {192, 192, 1}, {192, 768, 3}, {768, 192, 3}, {192, 160, 1}};
+
+static int find_shape(int cin, int cout, int taps)
+{
+    for (int i = 0; i < (int)(sizeof(kRowsShapes) / sizeof(kRowsShapes[0])); ++i)
+        if (kRowsShapes[i].cin == cin && kRowsShapes[i].cout == cout && kRowsShapes[i].taps == taps) return i;
+    return -1;
+}
+
+// weight [cout][cin][taps] fp32 -> slabW [cout/bn_w][tap][cin/8][bn_w][8], slabWT [cin/bn_wt][tap][cout/8][bn_wt][8]
+__global__ void __launch_bounds__(256)
+rows_pack_kernel(const float *__restrict__ w, int cout, int cin, int taps, int bn_w, int bn_wt,
+                 __nv_bfloat16 *__restrict__ slabW, __nv_bfloat16 *__restrict__ slabWT)
+{
+    const int total = cout * cin * taps;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int tap = i % taps, k = (i / taps) % cin, n = i / (taps * cin);
+        const __nv_bfloat16 wb = __float2bfloat16(w[i]);
+        slabW[((((size_t)(n / bn_w) * taps + tap) * (cin / 8) + k / 8) * bn_w + n % bn_w) * 8 + (k & 7)] = wb;
+        slabWT[((((size_t)(k / bn_wt) * taps + tap) * (cout / 8) + n / 8) * bn_wt + k % bn_wt) * 8 + (n & 7)] = wb;
+    }
+}
+
+template <int N, int KP, int NP, int LD, int TAPS, int DIR>
+static int run_gemm(const float *a, const void *slab, const float *bias, float *out, const int32_t *row_utt, int rows_pad,
+                    cudaStream_t st, const char *name)
+{
+    TcA ta{{a, a + KP, a + 2 * KP, a + 3 * KP}};
+    EpiRows e{bias, out, N};
+    return gemm_tc3<N, rows_bn(N), KP, NP, LD, TAPS, DIR, (KP % 96 == 0 ? 96 : KP / 2), 1>(
+        ta, (const __nv_bfloat16 *)slab, row_utt, rows_pad, e, st, name);
+}
+
+static int check_rows(const glow_rows_conv_call *c, int *shape)
+{
+    GLOW_REQUIRE(c != nullptr && c->row_utt != nullptr, GLOW_ERR_INVALID, "rows_conv: null call / row_utt");
+    GLOW_REQUIRE(c->rows_pad > 0 && c->rows_pad % kRowTile == 0, GLOW_ERR_INVALID,
+                 "rows_conv: rows_pad=%d must be a positive multiple of %d", c->rows_pad, kRowTile);
+    *shape = find_shape(c->cin, c->cout, c->taps);
+    GLOW_REQUIRE(*shape >= 0, GLOW_ERR_UNSUPPORTED,
+                 "rows_conv: no kernel built for cin=%d cout=%d taps=%d (built: 192->192 k5/k1, 192->768 k3, "
+                 "768->192 k3, 192->160 k1)", c->cin, c->cout, c->taps);
+    return GLOW_OK;
+}
+
+}  // namespace glow
+
+using namespace glow;
+
+extern "C" {
+
+size_t glow_rows_conv_slab_elems(int cin, int cout, int taps)
+{
+    return find_shape(cin, cout, taps) < 0 ? 0 : (size_t)cin * cout * taps;
+}
+
+int glow_rows_conv_pack(const glow_rows_conv_call *c, const float *weight, void *slab_w, void *slab_wt)
+{
+    int shape;
+    int rc = check_rows(c, &shape);
+    if (rc) return rc;
+    GLOW_REQUIRE(weight && slab_w && slab_wt, GLOW_ERR_INVALID, "rows_conv_pack: null pointer");
+    const int total = c->cin * c->cout * c->taps;
+    rows_pack_kernel<<<(total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs, 256, 0,
+                       (cudaStream_t)c->stream>>>(weight, c->cout, c->cin, c->taps, rows_bn(c->cout), rows_bn(c->cin),
+                                                  (__nv_bfloat16 *)slab_w, (__nv_bfloat16 *)slab_wt);
+    GLOW_CHECK_LAUNCH("rows_pack_kernel");
+    return GLOW_OK;
+}
+
+int glow_rows_conv_forward(const glow_rows_conv_call *c, const float *x, const void *slab_w, const float *bias, float *y)
+{
+    int shape;
+    int rc = check_rows(c, &shape);
+    if (rc) return rc;
+    GLOW_REQUIRE(x && slab_w && y, GLOW_ERR_INVALID, "rows_conv_forward: null pointer");
+    cudaStream_t st = (cudaStream_t)c->stream;
+    switch (shape) {
+    case 0: return run_gemm<192, 192, 1, 192, 5, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv5");
+    case 1: return run_gemm<192, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv1");
+    case 2: return run_gemm<768, 192, 1, 192, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_in");
+    case 3: return run_gemm<192, 192, 4, 768, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_out");
+    default: return run_gemm<160, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_project");
+    }
+}
+
+int glow_rows_conv_backward_data(const glow_rows_conv_call *c, const float *dy, const void *slab_wt, float *dx)
+{
+    int shape;
+    int rc = check_rows(c, &shape);
+    if (rc) return rc;
+    GLOW_REQUIRE(dy && slab_wt && dx, GLOW_ERR_INVALID, "rows_conv_backward_data: null pointer");
+    cudaStream_t st = (cudaStream_t)c->stream;
+    switch (shape) {      // the transposed GEMM: N = cin, K = cout, taps mirrored (DIR = -1)
+    case 0: return run_gemm<192, 192, 1, 192, 5, -1>(dy, slab_wt, nullptr, dx, c->row_utt, c->rows_pad, st, "enc_b_conv5");
+    case 1: return run_gemm<192, 192, 1, 192, 1, 0>(dy, slab_wt, nullptr, dx, c->row_utt, c->rows_pad, st, "enc_b_conv1");
+    case 2: return run_gemm<192, 192, 4, 768, 3, -1>(dy, slab_wt, nullptr, dx, c->row_utt, c->rows_pad, st, "enc_b_ffn_in");
+    case 3: return run_gemm<768, 192, 1, 192, 3, -1>(dy, slab_wt, nullptr, dx, c->row_utt, c->rows_pad, st, "enc_b_ffn_out");
+    default: return run_gemm<192, 160, 1, 160, 1, 0>(dy, slab_wt, nullptr, dx, c->row_utt, c->rows_pad, st, "enc_b_project");
+    }
+}
+
+int glow_rows_conv_backward_weight(const glow_rows_conv_call *c, const float *x, const float *dy, float *dw, float *dbias)
+{
+    int shape;
+    int rc = check_rows(c, &shape);
+    if (rc) return rc;
+    GLOW_REQUIRE(x && dy && dw, GLOW_ERR_INVALID, "rows_conv_backward_weight: null pointer");
+    cudaStream_t st = (cudaStream_t)c->stream;
+    const int center = (c->taps - 1) / 2;
+    // dw[tap][cin][cout] = sum_r x[r + tap - center]^T dy[r]  (x, dy already zero on guard rows)
+    rc = wgrad_gemm(st, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout, dw,
+                    c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
+    if (rc) return rc;
+    if (dbias != nullptr) {
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, st));
+        colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, st>>>(dy, c->cout, c->rows_pad, c->cout, dbias);
+        GLOW_CHECK_LAUNCH("colsum_kernel");
+    }
+    return GLOW_OK;
+}
+
+}  // extern "C"

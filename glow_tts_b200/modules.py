@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _lib, flow as _flow
+from . import _lib, flow as _flow, rows as _rows
 from .flat import FlatBuffer, offset_table
 from .hparams import load_hparams
 from .monotonic_align import maximum_path
@@ -474,11 +474,50 @@ class Encoder(torch.nn.Module):
         self.layer_Dict["Project"] = torch.nn.Conv1d(e.Channels, h.Sound.Mel_Dim * 2, 1)
         self.layer_Dict["Duration_Predictor"] = Duration_Predictor()
 
-    def forward(self, x, mask, speakers=None, prosodies=None, lengths=None):
+    def forward(self, x, mask, speakers=None, prosodies=None, lengths=None, host_lengths=None):
         _lib.require_cuda(mask, "Encoder mask")
+        # bf16 mode with the sentence lengths known on the host: packed-row encoder on the tcgen05 convs
+        if self.precision == "bf16" and host_lengths is not None and self.rows_supported:
+            return self._forward_rows(x, mask, speakers, lengths, host_lengths)
         # fp32 mode is the parity mode: keep cuDNN from silently using TF32 for the convs
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "fp32"):
             return self._forward(x, mask, speakers, lengths)
+
+    @property
+    def rows_supported(self):
+        """csrc/rows_conv.cu is built for the reference configuration (Hyper_Parameters.yaml:21-35)."""
+        h = _hp().Encoder
+        return (h.Channels == 192 and h.Prenet.Kernel_Size == 5 and h.Transformer.Conv.Kernel_Size == 3
+                and h.Transformer.Conv.Calc_Channels == 768 and self.mel_dim == 80)
+
+    def _forward_rows(self, tokens, mask, speakers, lengths, host_lengths):
+        """Modules.py:262-284 on packed token rows [rows, C] (rows.py): same arithmetic at every real
+        token; guard rows stand in for the padding the reference masks away."""
+        d = self.layer_Dict
+        dev = tokens.device
+        tr = _rows.token_rows(host_lengths, tokens.shape[1], dev)
+        tok = tokens.reshape(-1).index_select(0, tr.src_idx)
+        x = d["Embedding"](tok) * (math.sqrt(self.channels) * tr.valid)
+        pre = d["Prenet"]
+        y = x
+        for i in range(pre.stacks):
+            c = pre.layer_Dict["CLRD_%d" % i].layer_Dict
+            y = c["Dropout"](F.relu(c["LayerNorm"](_rows.rows_conv(y, c["Conv"], tr))))
+        x = _rows.rows_conv(y, pre.layer_Dict["Conv1x1"], tr) + x
+        tf = d["Transformer"]
+        for i in range(tf.stacks):
+            b = tf.layer_Dict["ANCRDCN_%d" % i].layer_Dict
+            a = b["Attention"].forward_rows(x, tr, lengths)
+            y = b["LayerNorm_0"](b["Dropout"](a) + x)
+            f = b["Dropout"](F.relu(_rows.rows_conv(y, b["Conv_0"], tr)))
+            f = b["Dropout"](_rows.rows_conv(f, b["Conv_1"], tr))
+            x = b["LayerNorm_1"](f + y)
+        ms = tr.unpack(_rows.rows_conv(x, d["Project"], tr)).transpose(1, 2)              # [B, 160, T]
+        mean, log_std = torch.split(ms, [self.mel_dim, self.mel_dim], dim=1)
+        xd = tr.unpack(x.detach()).transpose(1, 2)                                        # == (x * mask).detach()
+        spk = speakers.detach() if speakers is not None else None
+        log_dur = d["Duration_Predictor"](xd, mask, spk, None)
+        return mean, log_std, log_dur, mask
 
     def _forward(self, x, mask, speakers, lengths):
         d = self.layer_Dict
@@ -563,7 +602,7 @@ class GlowTTS(torch.nn.Module):
         m_len = _lib.device_ints(ml, torch.int32, dev)
 
         mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk, None,
-                                                           lengths=t_len)
+                                                           lengths=t_len, host_lengths=tl)
         dec = d["Decoder"]
         dec.host_lengths = ml
         try:

@@ -1,0 +1,122 @@
+"""Packed token rows for the text encoder.
+
+The reference runs the encoder on [B, C, T_x] tensors padded to the longest sentence and
+re-multiplies by the mask before every conv (Modules.py:554,567,570).  Here the tokens of a batch
+are packed along ONE row axis, channels-last -- the decoder's layout (csrc/flow_layout.cuh): two
+guard rows between sentences are the convs' zero padding, LayerNorm normalises the contiguous last
+dim (no transposes), and every conv is one tcgen05 GEMM launch (csrc/rows_conv.cu) that applies the
+mask as it loads and as it stores.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, flow as _flow
+
+
+class TokenRows:
+    """Row map of one batch of sentence lengths + the gather indices between [B, T] and rows."""
+
+    def __init__(self, lengths, t_max, device):
+        self.rm = _flow.row_map(lengths, device)
+        rm = self.rm
+        b = len(lengths)
+        self.batch, self.t_max, self.rows_pad = b, int(t_max), rm.rows_pad
+        row_utt = rm.row_utt.long()
+        valid = row_utt >= 0
+        self.valid = valid.to(torch.float32).unsqueeze(1)                         # [R, 1]
+        # rows -> flat (b, t) source index (guards read element 0 and are zeroed by `valid`)
+        self.src_idx = torch.where(valid, row_utt * self.t_max + rm.row_t.long(), torch.zeros_like(row_utt))
+        # flat (b, t) -> row (positions beyond a sentence read row 0, a guard row, and are zeroed by `tmask`)
+        t = torch.arange(self.t_max, device=device)[None, :]
+        lens = rm.utt_len.long()[:, None]
+        self.tmask = (t < lens).to(torch.float32)                                 # [B, T]
+        self.dst_idx = torch.where(t < lens, rm.utt_off.long()[:, None] + t, torch.zeros_like(t)).reshape(-1)
+
+    def pack(self, x_btc):
+        """[B, T, C] -> [rows_pad, C] (guard rows zero)."""
+        b, t, c = x_btc.shape
+        return x_btc.reshape(b * t, c).index_select(0, self.src_idx) * self.valid
+
+    def unpack(self, rows):
+        """[rows_pad, C] -> [B, T, C] (positions beyond each sentence zero)."""
+        c = rows.shape[1]
+        return rows.index_select(0, self.dst_idx).view(self.batch, self.t_max, c) * self.tmask.unsqueeze(2)
+
+
+_CACHE = {}
+
+
+def token_rows(lengths, t_max, device):
+    key = (tuple(int(n) for n in lengths), int(t_max), str(device))
+    tr = _CACHE.get(key)
+    if tr is None:
+        if len(_CACHE) > 64:
+            _CACHE.clear()
+        tr = _CACHE[key] = TokenRows(key[0], t_max, device)
+    return tr
+
+
+def _call(tr, cin, cout, taps, device):
+    c = _lib.RowsConvCall()
+    c.cin, c.cout, c.taps, c.rows_pad = cin, cout, taps, tr.rows_pad
+    c.row_utt = tr.rm.row_utt.data_ptr()
+    c.stream = torch.cuda.current_stream(device).cuda_stream
+    return c
+
+
+class RowsConvFn(torch.autograd.Function):
+    """y = mask * (bias + conv1d(mask * x)) on packed rows; weight in torch's Conv1d layout [cout, cin, taps]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, tr):
+        cout, cin, taps = weight.shape
+        dev = x.device
+        x = x.contiguous().float()
+        L = _lib.lib()
+        n = L.glow_rows_conv_slab_elems(cin, cout, taps)
+        if n == 0:
+            raise _lib.GlowCoreError("rows_conv: no kernel built for cin=%d cout=%d taps=%d" % (cin, cout, taps))
+        slab_w = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        slab_wt = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        y = torch.empty((tr.rows_pad, cout), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call = _call(tr, cin, cout, taps, dev)
+            _lib.check(L.glow_rows_conv_pack(ctypes.byref(call), _lib.ptr(weight.detach().contiguous()),
+                                             _lib.ptr(slab_w), _lib.ptr(slab_wt)), "glow_rows_conv_pack")
+            _lib.check(L.glow_rows_conv_forward(ctypes.byref(call), _lib.ptr(x), _lib.ptr(slab_w),
+                                                _lib.ptr(bias.detach().contiguous()) if bias is not None else None,
+                                                _lib.ptr(y)), "glow_rows_conv_forward")
+        ctx.tr, ctx.shape, ctx.has_bias = tr, (cin, cout, taps), bias is not None
+        ctx.save_for_backward(x, slab_wt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, slab_wt = ctx.saved_tensors
+        tr = ctx.tr
+        cin, cout, taps = ctx.shape
+        dev = dy.device
+        dy = dy.contiguous().float()
+        L = _lib.lib()
+        dx = dw = db = None
+        with torch.cuda.device(dev):
+            call = _call(tr, cin, cout, taps, dev)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty((tr.rows_pad, cin), dtype=torch.float32, device=dev)
+                _lib.check(L.glow_rows_conv_backward_data(ctypes.byref(call), _lib.ptr(dy), _lib.ptr(slab_wt),
+                                                          _lib.ptr(dx)), "glow_rows_conv_backward_data")
+            if ctx.needs_input_grad[1]:
+                xm, dym = x * tr.valid, dy * tr.valid          # the reduction runs over real rows only
+                dwt = torch.empty((taps, cin, cout), dtype=torch.float32, device=dev)
+                db = torch.empty(cout, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                _lib.check(L.glow_rows_conv_backward_weight(ctypes.byref(call), _lib.ptr(xm), _lib.ptr(dym),
+                                                            _lib.ptr(dwt), _lib.ptr(db)),
+                           "glow_rows_conv_backward_weight")
+                dw = dwt.permute(2, 1, 0)
+        return dx, dw, db, None
+
+
+def rows_conv(x, conv, tr):
+    """Apply a torch.nn.Conv1d's parameters to packed rows."""
+    return RowsConvFn.apply(x, conv.weight, conv.bias, tr)

@@ -102,6 +102,25 @@ class RPR_Multihead_Attention(torch.nn.Module):
         self.weight_K = torch.nn.Parameter(torch.randn(1, n_rel, self.calc_channels_per_head) * std)
         self.weight_V = torch.nn.Parameter(torch.randn(1, n_rel, self.calc_channels_per_head) * std)
 
+    def forward_rows(self, x, tr, lengths):
+        """Self-attention on packed token rows [rows, C] (rows.py): the four 1x1 convs run as tcgen05
+        GEMMs over the rows, the attention core on [B, C, T] views of their outputs."""
+        from . import rows as _rows
+        d = self.layer_Dict
+        q, k, v = (tr.unpack(_rows.rows_conv(x, d[n], tr)).transpose(1, 2) for n in ("Query", "Key", "Value"))
+        seed = self._next_seed()
+        lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        out, _ = _AttnCoreFn.apply(q, k, v, self.weight_K, self.weight_V, lengths, None, self.num_heads,
+                                   self.relative_postion_clipping_distance, self.dropout_rate, seed, False)
+        return _rows.rows_conv(tr.pack(out.transpose(1, 2)), d["Projection"], tr)
+
+    def _next_seed(self):
+        if not (self.training and self.dropout_rate > 0):
+            return 0
+        self._calls += 1
+        return ((int(torch.initial_seed()) * 0x2545F491 + self._calls * 0x9E3779B1 + id(self) % 65521)
+                & 0x7FFFFFFFFFFFFFFF) or 1
+
     def forward(self, queries, keys=None, values=None, masks=None, lengths=None, need_alignments=True):
         assert keys is None and values is None, "Relative position is for self-attention."
         _lib.require_cuda(queries, "queries")
@@ -109,11 +128,7 @@ class RPR_Multihead_Attention(torch.nn.Module):
         q = d["Query"](queries)
         k = d["Key"](queries)
         v = d["Value"](queries)
-        seed = 0
-        if self.training and self.dropout_rate > 0:
-            self._calls += 1
-            seed = ((int(torch.initial_seed()) * 0x2545F491 + self._calls * 0x9E3779B1 + id(self) % 65521)
-                    & 0x7FFFFFFFFFFFFFFF) or 1
+        seed = self._next_seed()
         if lengths is not None:
             lengths = lengths.to(device=q.device, dtype=torch.int32).contiguous()
         out, align = _AttnCoreFn.apply(q, k, v, self.weight_K, self.weight_V, lengths, masks, self.num_heads,

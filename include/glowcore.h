@@ -210,6 +210,42 @@ int glow_rpr_attention_backward(const glow_attn_call *call, const float *dout, c
                                 float *dwk, float *dwv);
 
 /* ------------------------------------------------------------------------ *
+ * Text-encoder convolutions over packed token rows
+ * replaces: the Conv1d calls of Modules.py:461-489 (CLRD), :509-573 (ANCRDCN
+ *           Conv_0 / Conv_1), RPR_MHA.py:59-66,82-93 (Query/Key/Value/Projection)
+ *           and Modules.py:252 (Project), including the `x * mask` in front of
+ *           each and the mask on the result, and their autograd backward.
+ * x, y, dx, dy are fp32 [rows_pad, C] over the same packed row axis the decoder
+ * uses (row_utt[row] < 0 on guard / tail rows): guard rows are read as zeros
+ * and written as zeros, so they are the convs' zero padding.  Operands are
+ * rounded to bf16 on the way into the tensor cores, accumulation is fp32.
+ * Built shapes (cin, cout, taps): (192,192,5) (192,192,1) (192,768,3)
+ * (768,192,3) (192,160,1); anything else returns GLOW_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int cin, cout, taps;
+    int rows_pad;
+    const int32_t *row_utt;
+    glow_stream_t stream;
+} glow_rows_conv_call;
+
+/* bf16 elements of ONE slab image of the weight (0: shape not built). */
+size_t glow_rows_conv_slab_elems(int cin, int cout, int taps);
+/* weight [cout, cin, taps] fp32 (torch Conv1d layout) -> slab_w (forward operand) and slab_wt
+ * (data-gradient operand), each glow_rows_conv_slab_elems bf16 elements. */
+int glow_rows_conv_pack(const glow_rows_conv_call *call, const float *weight, void *slab_w, void *slab_wt);
+/* y = mask * (bias + conv(mask * x)); bias may be NULL. */
+int glow_rows_conv_forward(const glow_rows_conv_call *call, const float *x, const void *slab_w,
+                           const float *bias, float *y);
+/* dx = mask * conv^T(mask * dy). */
+int glow_rows_conv_backward_data(const glow_rows_conv_call *call, const float *dy, const void *slab_wt,
+                                 float *dx);
+/* dw [taps, cin, cout] = sum_rows x[row + tap - c]^T dy[row] (overwritten), dbias [cout] = column sums
+ * of dy (overwritten; may be NULL).  x and dy must already be zero on guard rows. */
+int glow_rows_conv_backward_weight(const glow_rows_conv_call *call, const float *x, const float *dy,
+                                   float *dw, float *dbias);
+
+/* ------------------------------------------------------------------------ *
  * Optimizer step over the flat parameter / gradient buffers
  * replaces: torch.nn.utils.clip_grad_norm_(max_norm) at Train.py:227-231 and
  *           RAdam.step (Radam.py:25-90) -- the rectification scalars N_sma /

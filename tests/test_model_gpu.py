@@ -135,7 +135,7 @@ def test_graph_replays_draw_fresh_dropout_masks():
         torch.cuda.synchronize()
         losses.append(float(graphed.last["mle"]))
     assert len(set(losses)) == 3, losses
-    assert max(losses) - min(losses) < 0.2 * abs(losses[0]), losses
+    assert max(losses) - min(losses) < 0.5 * abs(losses[0]), losses          # same weights, different masks
 
 
 def test_state_dict_roundtrip_and_cpu_is_refused():

@@ -38,11 +38,19 @@ class AttnCall(ctypes.Structure):            # glow_attn_call
 
 
 class RowsConvCall(ctypes.Structure):        # glow_rows_conv_call
-    _fields_ = [("cin", _I), ("cout", _I), ("taps", _I), ("rows_pad", _I), ("row_utt", _P), ("stream", _P)]
+    _fields_ = [("cin", _I), ("cout", _I), ("taps", _I), ("rows_pad", _I), ("row_utt", _P),
+                ("relu", _I), ("p_out", _F), ("seed_out", _U64), ("step_dev", _P), ("stream", _P)]
+
+
+class RowsNormCall(ctypes.Structure):        # glow_rows_norm_call
+    _fields_ = [("rows_pad", _I), ("channels", _I), ("row_utt", _P), ("eps", _F),
+                ("p_in", _F), ("seed_in", _U64), ("relu", _I), ("p_out", _F), ("seed_out", _U64),
+                ("step_dev", _P), ("stream", _P)]
 
 
 _PCFG, _PCALL, _PATTN = ctypes.POINTER(FlowConfig), ctypes.POINTER(FlowCall), ctypes.POINTER(AttnCall)
 _PROWS = ctypes.POINTER(RowsConvCall)
+_PNORM = ctypes.POINTER(RowsNormCall)
 
 # name -> (restype, argtypes); kept in step with include/glowcore.h
 # (tests/test_abi.py parses the header and checks every declared symbol is here
@@ -72,6 +80,9 @@ SIGNATURES = {
     "glow_rows_conv_forward": (_I, [_PROWS, _P, _P, _P, _P]),
     "glow_rows_conv_backward_data": (_I, [_PROWS, _P, _P, _P]),
     "glow_rows_conv_backward_weight": (_I, [_PROWS, _P, _P, _P, _P]),
+    "glow_rows_act_backward": (_I, [_P, _I, _I, _I, _F, _U64, _P, _P, _P, _P, _P]),
+    "glow_rows_norm_forward": (_I, [_PNORM, _P, _P, _P, _P, _P, _P, _P]),
+    "glow_rows_norm_backward": (_I, [_PNORM, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_sqnorm": (_I, [_P, _Z, _P, _P]),
     "glow_radam_step": (_I, [_P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _F, _F, _P, _P, _P]),
     "glow_radam_step_dev": (_I, [_P, _P, _P, _P, _Z, _P, _P, _P, _P]),

@@ -143,13 +143,20 @@ struct DropCfg {
     // keep bits of packed columns (n, n+1), n even: bit 0 -> column n, bit 1 -> column n+1
     __device__ __forceinline__ uint32_t thresh() const { return (uint32_t)(p * 65536.f + 0.5f); }
     __device__ __forceinline__ float scale() const { return 65536.f / (65536.f - (float)thresh()); }
-    __device__ __forceinline__ uint32_t keep2(int row, int n) const
+    __device__ __forceinline__ uint32_t seed32() const
     {
         uint64_t sd = seed;
         if (step_dev != nullptr) sd ^= __ldg(step_dev) * 0xD6E8FEB86659FD93ull;
-        const uint32_t s32 = (uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B1u);
-        const uint32_t idx = ((uint32_t)base + (uint32_t)row) * (uint32_t)(kG / 2) + (uint32_t)(n >> 1);
-        const uint32_t h = hash32(idx * 0x9E3779B1u + s32);
+        return (uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B1u);
+    }
+    // index of the column pair (n, n+1) of `row` in this layer's counter space
+    __device__ __forceinline__ uint32_t pair_index(int row, int n) const
+    {
+        return ((uint32_t)base + (uint32_t)row) * (uint32_t)(kG / 2) + (uint32_t)(n >> 1);
+    }
+    __device__ __forceinline__ uint32_t keep2(int row, int n) const
+    {
+        const uint32_t h = hash32(pair_index(row, n) * 0x9E3779B1u + seed32());
         const uint32_t t = thresh();
         return ((h & 0xffffu) >= t ? 1u : 0u) | ((h >> 16) >= t ? 2u : 0u);
     }
@@ -197,23 +204,34 @@ struct EpiGate {
     // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
     template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
     {
-        const int b = utt;
-        float bs[NV], ts[NV], acts[NV / 2];
-        ld_vec<NV>(bias + n0, bs);
+        const bool m = utt >= 0;
+        float pre[NV], ts[NV], acts[NV / 2];
+        ld_vec<NV>(bias + n0, pre);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) pre[j] += v[j];
+        if (drop.seed != 0) {                                  // uniform over the launch
+            const uint32_t t = drop.thresh(), s32 = drop.seed32(), i0 = drop.pair_index(row, n0);
+            const float sc = drop.scale();
+#pragma unroll
+            for (int j = 0; j < NV / 2; ++j) {
+                const uint32_t h = hash32((i0 + (uint32_t)j) * 0x9E3779B1u + s32);
+                pre[2 * j] = (h & 0xffffu) >= t ? pre[2 * j] * sc : 0.f;
+                pre[2 * j + 1] = (h >> 16) >= t ? pre[2 * j + 1] * sc : 0.f;
+            }
+        }
+        if (spkb != nullptr) {                                 // uniform: SE mode
+            float sv[NV];
+            ld_vec<NV>(spkb + (size_t)(m ? utt : 0) * kG + n0, sv);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) pre[j] += sv[j];
+        }
 #pragma unroll
         for (int j = 0; j < NV / 2; ++j) {
-            const int n = n0 + 2 * j;
-            float t = 0.f, s = 0.f;
-            if (b >= 0) {
-                float pt = v[2 * j] + bs[2 * j], ps = v[2 * j + 1] + bs[2 * j + 1];
-                drop.apply2(pt, ps, row, n);
-                if (spkb != nullptr) { pt += spkb[(size_t)b * kG + n]; ps += spkb[(size_t)b * kG + n + 1]; }
-                t = tanh_t<FAST>(pt);
-                s = sigmoid_t<FAST>(ps);
-            }
+            const float t = m ? tanh_t<FAST>(pre[2 * j]) : 0.f;
+            const float sg = m ? sigmoid_t<FAST>(pre[2 * j + 1]) : 0.f;
             ts[2 * j] = t;
-            ts[2 * j + 1] = s;
-            acts[j] = t * s;
+            ts[2 * j + 1] = sg;
+            acts[j] = t * sg;
         }
         st_vec<NV>(TS + (size_t)row * kG + n0, ts);
         st_vec<NV / 2>(ACTS + (size_t)row * kH + (n0 >> 1), acts);

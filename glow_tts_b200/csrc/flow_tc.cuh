@@ -46,6 +46,8 @@ constexpr int kTcPitch = 133 * 16;          // slab pitch in bytes: 133 rows -> 
 constexpr int kTcThreads = 512;             // 16 warps: 0-3 A loaders, 4/6 weight producers, 5 MMA, 8-15 epilogue
 constexpr int kTcLoaders = 128;             // threads of the four A-loader warps (120 of them copy)
 constexpr int kTcLoadActive = 120;          // = 24*5 = 20*6 = 10*12: a whole number of rows for K panels of 192/160/80
+constexpr int kTcFirstThreads = 384;        // the CTA's FIRST panel is staged by the loaders and the (still idle) epilogue warps
+constexpr int kTcFirstActive = 360;         // = 24*15 = 20*18 = 10*36
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcMaxStages = 8;
 constexpr int kTcSmemCap = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (barriers are static)
@@ -102,6 +104,76 @@ struct TcCfg {
                                                       : (2 * BN <= 256) ? 256u : 512u;
 };
 
+// Stage one A panel (kTcRows rows x KP columns, fp32 or bf16 in HBM) into its slab layout.
+// `idx` of `ACTIVE` participating threads: thread -> fixed 16 B column chunk c, rows r0, r0 + step, ...
+// Register-staged: LDG.128 batches (coalesced along the row) -> STS.128 into the slabs.  (LDGSTS with
+// per-lane scattered shared destinations and 16 B-row TMA boxes both run at about one 16 B row per
+// cycle: profiles/ubench_r01.md.)  Rows outside [0, rows_pad) (first / last tile) read a zero guard
+// row instead: rows 0-1 and the last rows of every packed buffer are guards (flow_layout.cuh).
+template <class Cfg, int LD, int AMODE, int ACTIVE>
+__device__ __forceinline__ void stage_panel(const void *base, uint32_t panel_smem, int idx, int row0, int rows_pad,
+                                            const int32_t *__restrict__ row_utt)
+{
+    constexpr int KPCH = Cfg::kKpch;
+    constexpr int kStep = ACTIVE / KPCH;
+    constexpr int kIters = (kTcRows + kStep - 1) / kStep;
+    static_assert(ACTIVE % KPCH == 0, "loader mapping");
+    if (idx >= ACTIVE) return;
+    const int c = idx % KPCH, r0 = idx / KPCH;
+    const bool interior = row0 >= 0 && row0 + kTcRows <= rows_pad;
+    const uint32_t dst = panel_smem + (uint32_t)c * kTcPitch + (uint32_t)r0 * 16u;
+    if constexpr (AMODE == 0) {
+        const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(base) + c * 8;
+        constexpr int kBatch = kIters < 14 ? kIters : 14;
+#pragma unroll
+        for (int k0 = 0; k0 < kIters; k0 += kBatch) {
+            uint4 t[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int r = r0 + (k0 + k) * kStep;
+                if (k0 + k < kIters && r < kTcRows) {
+                    int row = row0 + r;
+                    if (!interior) row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
+                    t[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * LD));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)
+                if (k0 + k < kIters && r0 + (k0 + k) * kStep < kTcRows)
+                    st_shared16(dst + (uint32_t)((k0 + k) * kStep * 16), t[k]);
+        }
+    } else {
+        const float *src = reinterpret_cast<const float *>(base) + c * 8;
+        constexpr int kBatch = kIters < 7 ? kIters : 7;
+#pragma unroll
+        for (int k0 = 0; k0 < kIters; k0 += kBatch) {
+            float4 t0[kBatch], t1[kBatch];
+            int u[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int r = r0 + (k0 + k) * kStep;
+                if (k0 + k < kIters && r < kTcRows) {
+                    int row = row0 + r;
+                    row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
+                    const float4 *g = reinterpret_cast<const float4 *>(src + (size_t)row * LD);
+                    t0[k] = __ldg(g);
+                    t1[k] = __ldg(g + 1);
+                    u[k] = __ldg(row_utt + row);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)
+                if (k0 + k < kIters && r0 + (k0 + k) * kStep < kTcRows) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (u[k] >= 0)
+                        v = make_uint4(pack_bf16x2(t0[k].x, t0[k].y), pack_bf16x2(t0[k].z, t0[k].w),
+                                       pack_bf16x2(t1[k].x, t1[k].y), pack_bf16x2(t1[k].z, t1[k].w));
+                    st_shared16(dst + (uint32_t)((k0 + k) * kStep * 16), v);
+                }
+        }
+    }
+}
+
 template <class Cfg, int N, int BN, int KP, int NP, int LD, int TAPS, int DIR, int KS, int AMODE, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int32_t *__restrict__ row_utt,
@@ -113,6 +185,7 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
     constexpr int NSL = Cfg::kSlices;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t a_full[2], a_empty[2], b_full[kTcMaxStages], b_empty[kTcMaxStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t a_first;                 // the CTA's first panel: staged by loaders + epilogue warps together
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,6 +198,7 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps);
         }
         for (int i = 0; i < S; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&a_first, kTcFirstThreads);
         mbar_fence_init();
     }
     if (warp == 5) tmem_alloc(&s_tmem, Cfg::kCols);
@@ -135,78 +209,23 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
     long long *dbg = (dbg_all != nullptr && blockIdx.x == gridDim.x / 2) ? dbg_all : nullptr;
     if (dbg && tid == 0) dbg[0] = clock64();
 
-    if (warp < 4) {                                                    // ---- A loaders (128 threads, 120 copy)
-        // thread -> fixed 16 B column chunk c, rows r0, r0 + kRowsStep, ...: every copy of a panel is
-        // base + compile-time offset.
-        const bool active = tid < kTcLoadActive;
-        const int c = tid % KPCH, r0 = tid / KPCH;
+    if (warp < 4) {                                                    // ---- A loaders (128 threads)
         uint32_t pc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int row0 = (item / NSL) * 128 - kGuard;
-            const bool interior = row0 >= 0 && row0 + kTcRows <= rows_pad;
 #pragma unroll 1
             for (int p = 0; p < NP; ++p, ++pc) {
                 const uint32_t buf = pc & 1u;
-                if (pc >= 2) mbar_wait(&a_empty[buf], ((pc >> 1) - 1u) & 1u);
-                if (active) {
-                    const uint32_t dst = smem_u32(smem) + buf * Cfg::kPanelBytes + (uint32_t)c * kTcPitch + (uint32_t)r0 * 16u;
-                    // register-staged: LDG.128 batches (coalesced along the row) -> STS.128 into the slabs.
-                    // (LDGSTS with per-lane scattered shared destinations and 16 B-row TMA boxes both run
-                    // at about one 16 B row per cycle: profiles/ubench_r01.md.)  Rows outside [0, rows_pad)
-                    // (first / last tile) read a zero guard row instead: rows 0-1 and the last rows of every
-                    // packed buffer are guards (flow_layout.cuh).
-                    if constexpr (AMODE == 0) {
-                        const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(a.p[p]) + c * 8;
-                        constexpr int kBatch = 14;
-#pragma unroll
-                        for (int k0 = 0; k0 < Cfg::kLoadIters; k0 += kBatch) {
-                            uint4 t[kBatch];
-#pragma unroll
-                            for (int k = 0; k < kBatch; ++k) {
-                                const int r = r0 + (k0 + k) * Cfg::kRowsStep;
-                                if (k0 + k < Cfg::kLoadIters && r < kTcRows) {
-                                    int row = row0 + r;
-                                    if (!interior) row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
-                                    t[k] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * LD));
-                                }
-                            }
-#pragma unroll
-                            for (int k = 0; k < kBatch; ++k)
-                                if (k0 + k < Cfg::kLoadIters && r0 + (k0 + k) * Cfg::kRowsStep < kTcRows)
-                                    st_shared16(dst + (uint32_t)((k0 + k) * Cfg::kRowsStep * 16), t[k]);
-                        }
-                    } else {
-                        const float *src = reinterpret_cast<const float *>(a.p[p]) + c * 8;
-                        constexpr int kBatch = 7;
-#pragma unroll
-                        for (int k0 = 0; k0 < Cfg::kLoadIters; k0 += kBatch) {
-                            float4 t0[kBatch], t1[kBatch];
-                            int u[kBatch];
-#pragma unroll
-                            for (int k = 0; k < kBatch; ++k) {
-                                const int r = r0 + (k0 + k) * Cfg::kRowsStep;
-                                if (k0 + k < Cfg::kLoadIters && r < kTcRows) {
-                                    int row = row0 + r;
-                                    row = row < 0 ? 0 : (row >= rows_pad ? rows_pad - 1 : row);
-                                    const float4 *g = reinterpret_cast<const float4 *>(src + (size_t)row * LD);
-                                    t0[k] = __ldg(g);
-                                    t1[k] = __ldg(g + 1);
-                                    u[k] = __ldg(row_utt + row);
-                                }
-                            }
-#pragma unroll
-                            for (int k = 0; k < kBatch; ++k)
-                                if (k0 + k < Cfg::kLoadIters && r0 + (k0 + k) * Cfg::kRowsStep < kTcRows) {
-                                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                                    if (u[k] >= 0)
-                                        v = make_uint4(pack_bf16x2(t0[k].x, t0[k].y), pack_bf16x2(t0[k].z, t0[k].w),
-                                                       pack_bf16x2(t1[k].x, t1[k].y), pack_bf16x2(t1[k].z, t1[k].w));
-                                    st_shared16(dst + (uint32_t)((k0 + k) * Cfg::kRowsStep * 16), v);
-                                }
-                        }
-                    }
+                const uint32_t dst = smem_u32(smem) + buf * Cfg::kPanelBytes;
+                if (pc == 0) {                                         // shared with the epilogue warps (below)
+                    stage_panel<Cfg, LD, AMODE, kTcFirstActive>(a.p[p], dst, tid, row0, rows_pad, row_utt);
+                    fence_proxy_async();                               // generic-proxy writes -> tcgen05.mma reads
+                    mbar_arrive(&a_first);
+                    continue;
                 }
-                fence_proxy_async();                                   // generic-proxy writes -> tcgen05.mma reads
+                if (pc >= 2) mbar_wait(&a_empty[buf], ((pc >> 1) - 1u) & 1u);
+                stage_panel<Cfg, LD, AMODE, kTcLoadActive>(a.p[p], dst, tid, row0, rows_pad, row_utt);
+                fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
             }
         }
@@ -244,7 +263,8 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
 #pragma unroll 1
                 for (int p = 0; p < NP; ++p, ++pc) {
                     const uint32_t buf = pc & 1u;
-                    mbar_wait(&a_full[buf], (pc >> 1) & 1u);
+                    if (pc == 0) mbar_wait(&a_first, 0);
+                    else mbar_wait(&a_full[buf], ((pc >> 1) - (buf ^ 1u)) & 1u);   // buffer 0's first fill went through a_first
                     tc_fence_after();
                     if (dbg && it < 2 && p == 0) dbg[8 + it * 8] = clock64();
                     // descriptors advance in 16 B units: one row per tap step, 2 slabs per 16-wide K step
@@ -279,6 +299,12 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
         const int half = (warp >> 2) & 1;                              // even / odd 32-column chunks of the slice
         float *stg = sStage + (warp - 8) * kTcStagingFloats;
         const int sub_r = lane >> 2, sub_c = (lane & 3) * 8;           // transposed ownership: 8 rows x 4 column octets
+        if (blockIdx.x < n_items) {                                    // idle until the first accumulator: help stage panel 0
+            stage_panel<Cfg, LD, AMODE, kTcFirstActive>(a.p[0], smem_u32(smem), tid - 256 + kTcLoaders,
+                                                        (blockIdx.x / NSL) * 128 - kGuard, rows_pad, row_utt);
+            fence_proxy_async();
+            mbar_arrive(&a_first);
+        }
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t acc = it & 1u;

@@ -12,15 +12,34 @@
 
 namespace glow {
 
-// y = mask * (acc + bias)   (bias null: data-gradient GEMM)
+// y = mask * Dropout(ReLU?(acc + bias))   (bias null, no activation: data-gradient GEMM)
+// The dropout stream is the one glow_rows_act_backward replays (rows_norm.cu: RowsDrop).
 struct EpiRows {
     const float *bias; float *out; int ldo;
+    int relu; float p; uint64_t seed; const uint64_t *step_dev;
     template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
     {
         float b[NV], o[NV];
         if (bias != nullptr) ld_vec<NV>(bias + n0, b);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) o[j] = utt >= 0 ? v[j] + (bias != nullptr ? b[j] : 0.f) : 0.f;
+        for (int j = 0; j < NV; ++j) {
+            float t = v[j] + (bias != nullptr ? b[j] : 0.f);
+            if (relu) t = fmaxf(t, 0.f);
+            o[j] = utt >= 0 ? t : 0.f;
+        }
+        if (seed != 0) {
+            uint64_t sd = seed;
+            if (step_dev != nullptr) sd ^= __ldg(step_dev) * 0xD6E8FEB86659FD93ull;
+            const uint32_t s32 = (uint32_t)sd ^ ((uint32_t)(sd >> 32) * 0x9E3779B1u);
+            const uint32_t th = (uint32_t)(p * 65536.f + 0.5f);
+            const float sc = 65536.f / (65536.f - (float)th);
+#pragma unroll
+            for (int j = 0; j < NV / 2; ++j) {
+                const uint32_t h = hash32(((uint32_t)row * (uint32_t)(ldo >> 1) + (uint32_t)((n0 >> 1) + j)) * 0x9E3779B1u + s32);
+                o[2 * j] = (h & 0xffffu) >= th ? o[2 * j] * sc : 0.f;
+                o[2 * j + 1] = (h >> 16) >= th ? o[2 * j + 1] * sc : 0.f;
+            }
+        }
         st_vec<NV>(out + (size_t)row * ldo + n0, o);
     }
 };
@@ -54,10 +73,14 @@ rows_pack_kernel(const float *__restrict__ w, int cout, int cin, int taps, int b
 
 template <int N, int KP, int NP, int LD, int TAPS, int DIR>
 static int run_gemm(const float *a, const void *slab, const float *bias, float *out, const int32_t *row_utt, int rows_pad,
-                    cudaStream_t st, const char *name)
+                    cudaStream_t st, const char *name, const glow_rows_conv_call *c = nullptr)
 {
     TcA ta{{a, a + KP, a + 2 * KP, a + 3 * KP}};
-    EpiRows e{bias, out, N};
+    EpiRows e{bias, out, N, 0, 0.f, 0, nullptr};
+    if (c != nullptr) {                               // forward: fused activation
+        e.relu = c->relu;
+        if (c->p_out > 0.f && c->seed_out != 0) { e.p = c->p_out; e.seed = c->seed_out; e.step_dev = c->step_dev; }
+    }
     return gemm_tc3<N, rows_bn(N), KP, NP, LD, TAPS, DIR, (KP % 96 == 0 ? 96 : KP / 2), 1>(
         ta, (const __nv_bfloat16 *)slab, row_utt, rows_pad, e, st, name);
 }
@@ -107,11 +130,11 @@ int glow_rows_conv_forward(const glow_rows_conv_call *c, const float *x, const v
     GLOW_REQUIRE(x && slab_w && y, GLOW_ERR_INVALID, "rows_conv_forward: null pointer");
     cudaStream_t st = (cudaStream_t)c->stream;
     switch (shape) {
-    case 0: return run_gemm<192, 192, 1, 192, 5, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv5");
-    case 1: return run_gemm<192, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv1");
-    case 2: return run_gemm<768, 192, 1, 192, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_in");
-    case 3: return run_gemm<192, 192, 4, 768, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_out");
-    default: return run_gemm<160, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_project");
+    case 0: return run_gemm<192, 192, 1, 192, 5, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv5", c);
+    case 1: return run_gemm<192, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_conv1", c);
+    case 2: return run_gemm<768, 192, 1, 192, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_in", c);
+    case 3: return run_gemm<192, 192, 4, 768, 3, +1>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_ffn_out", c);
+    default: return run_gemm<160, 192, 1, 192, 1, 0>(x, slab_w, bias, y, c->row_utt, c->rows_pad, st, "enc_project", c);
     }
 }
 

@@ -490,29 +490,45 @@ class Encoder(torch.nn.Module):
         return (h.Channels == 192 and h.Prenet.Kernel_Size == 5 and h.Transformer.Conv.Kernel_Size == 3
                 and h.Transformer.Conv.Calc_Channels == 768 and self.mel_dim == 80)
 
+    def _site_seed(self, site):
+        """Dropout stream of one call site of this step (0 in eval); csrc kernels mix in the device step counter."""
+        if not self.training:
+            return 0
+        return ((int(torch.initial_seed()) * 0x9E3779B1 + self._calls * 0x85EBCA77 + site * 0xC2B2AE3D + 1)
+                & 0x7FFFFFFFFFFFFFFF) or 1
+
     def _forward_rows(self, tokens, mask, speakers, lengths, host_lengths):
         """Modules.py:262-284 on packed token rows [rows, C] (rows.py): same arithmetic at every real
-        token; guard rows stand in for the padding the reference masks away."""
+        token; guard rows stand in for the padding the reference masks away.  Every op writes guard
+        rows as zeros, so convs need no separate `* mask` pass."""
         d = self.layer_Dict
         dev = tokens.device
+        h = _hp().Encoder
+        self._calls = getattr(self, "_calls", 0) + 1
         tr = _rows.token_rows(host_lengths, tokens.shape[1], dev)
         tok = tokens.reshape(-1).index_select(0, tr.src_idx)
         x = d["Embedding"](tok) * (math.sqrt(self.channels) * tr.valid)
         pre = d["Prenet"]
+        p_pre = float(h.Prenet.Dropout_Rate)
         y = x
+        site = 0
         for i in range(pre.stacks):
             c = pre.layer_Dict["CLRD_%d" % i].layer_Dict
-            y = c["Dropout"](F.relu(c["LayerNorm"](_rows.rows_conv(y, c["Conv"], tr))))
-        x = _rows.rows_conv(y, pre.layer_Dict["Conv1x1"], tr) + x
+            y = _rows.rows_conv(y, c["Conv"], tr, x_masked=True)
+            site += 1
+            y = _rows.rows_norm(y, None, c["LayerNorm"], tr, relu=True, p_out=p_pre, seed_out=self._site_seed(site))
+        x = _rows.rows_conv(y, pre.layer_Dict["Conv1x1"], tr, x_masked=True) + x
         tf = d["Transformer"]
+        p_tf = float(h.Transformer.Dropout_Rate)
         for i in range(tf.stacks):
             b = tf.layer_Dict["ANCRDCN_%d" % i].layer_Dict
             a = b["Attention"].forward_rows(x, tr, lengths)
-            y = b["LayerNorm_0"](b["Dropout"](a) + x)
-            f = b["Dropout"](F.relu(_rows.rows_conv(y, b["Conv_0"], tr)))
-            f = b["Dropout"](_rows.rows_conv(f, b["Conv_1"], tr))
-            x = b["LayerNorm_1"](f + y)
-        ms = tr.unpack(_rows.rows_conv(x, d["Project"], tr)).transpose(1, 2)              # [B, 160, T]
+            y = _rows.rows_norm(a, x, b["LayerNorm_0"], tr, p_in=p_tf, seed_in=self._site_seed(site + 1))
+            f = _rows.rows_conv(y, b["Conv_0"], tr, relu=True, p=p_tf, seed=self._site_seed(site + 2), x_masked=True)
+            f = _rows.rows_conv(f, b["Conv_1"], tr, x_masked=True)
+            x = _rows.rows_norm(f, y, b["LayerNorm_1"], tr, p_in=p_tf, seed_in=self._site_seed(site + 3))
+            site += 3
+        ms = tr.unpack(_rows.rows_conv(x, d["Project"], tr, x_masked=True)).transpose(1, 2)              # [B, 160, T]
         mean, log_std = torch.split(ms, [self.mel_dim, self.mel_dim], dim=1)
         xd = tr.unpack(x.detach()).transpose(1, 2)                                        # == (x * mask).detach()
         spk = speakers.detach() if speakers is not None else None

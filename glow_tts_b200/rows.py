@@ -57,19 +57,22 @@ def token_rows(lengths, t_max, device):
     return tr
 
 
-def _call(tr, cin, cout, taps, device):
+def _call(tr, cin, cout, taps, device, relu=False, p=0.0, seed=0):
     c = _lib.RowsConvCall()
     c.cin, c.cout, c.taps, c.rows_pad = cin, cout, taps, tr.rows_pad
     c.row_utt = tr.rm.row_utt.data_ptr()
+    c.relu, c.p_out, c.seed_out = int(bool(relu)), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF
+    c.step_dev = _lib.step_counter_ptr(device) if seed else None
     c.stream = torch.cuda.current_stream(device).cuda_stream
     return c
 
 
 class RowsConvFn(torch.autograd.Function):
-    """y = mask * (bias + conv1d(mask * x)) on packed rows; weight in torch's Conv1d layout [cout, cin, taps]."""
+    """y = mask * Dropout(ReLU?(bias + conv1d(mask * x))) on packed rows; weight in torch's Conv1d layout
+    [cout, cin, taps].  seed == 0 disables the dropout (eval)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, tr):
+    def forward(ctx, x, weight, bias, tr, relu, p, seed):
         cout, cin, taps = weight.shape
         dev = x.device
         x = x.contiguous().float()
@@ -80,43 +83,121 @@ class RowsConvFn(torch.autograd.Function):
         slab_w = torch.empty(n, dtype=torch.bfloat16, device=dev)
         slab_wt = torch.empty(n, dtype=torch.bfloat16, device=dev)
         y = torch.empty((tr.rows_pad, cout), dtype=torch.float32, device=dev)
+        if not (p > 0 and seed):
+            p, seed = 0.0, 0
         with torch.cuda.device(dev):
-            call = _call(tr, cin, cout, taps, dev)
+            call = _call(tr, cin, cout, taps, dev, relu, p, seed)
             _lib.check(L.glow_rows_conv_pack(ctypes.byref(call), _lib.ptr(weight.detach().contiguous()),
                                              _lib.ptr(slab_w), _lib.ptr(slab_wt)), "glow_rows_conv_pack")
             _lib.check(L.glow_rows_conv_forward(ctypes.byref(call), _lib.ptr(x), _lib.ptr(slab_w),
                                                 _lib.ptr(bias.detach().contiguous()) if bias is not None else None,
                                                 _lib.ptr(y)), "glow_rows_conv_forward")
-        ctx.tr, ctx.shape, ctx.has_bias = tr, (cin, cout, taps), bias is not None
-        ctx.save_for_backward(x, slab_wt)
+        ctx.tr, ctx.shape, ctx.has_bias, ctx.act = tr, (cin, cout, taps), bias is not None, (bool(relu), p, seed)
+        ctx.save_for_backward(x, slab_wt, y if (relu or seed) else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, slab_wt = ctx.saved_tensors
+        x, slab_wt, y = ctx.saved_tensors
         tr = ctx.tr
         cin, cout, taps = ctx.shape
+        relu, p, seed = ctx.act
         dev = dy.device
         dy = dy.contiguous().float()
         L = _lib.lib()
         dx = dw = db = None
         with torch.cuda.device(dev):
             call = _call(tr, cin, cout, taps, dev)
+            st = _lib.stream_ptr(dev)
+            # gradient w.r.t. the conv result: through the fused ReLU / dropout, zero on guard rows
+            g = torch.empty_like(dy)
+            _lib.check(L.glow_rows_act_backward(tr.rm.row_utt.data_ptr(), tr.rows_pad, cout, int(relu), float(p),
+                                                int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                _lib.step_counter_ptr(dev) if seed else None,
+                                                _lib.ptr(dy), _lib.ptr(y), _lib.ptr(g), st), "glow_rows_act_backward")
             if ctx.needs_input_grad[0]:
                 dx = torch.empty((tr.rows_pad, cin), dtype=torch.float32, device=dev)
-                _lib.check(L.glow_rows_conv_backward_data(ctypes.byref(call), _lib.ptr(dy), _lib.ptr(slab_wt),
+                _lib.check(L.glow_rows_conv_backward_data(ctypes.byref(call), _lib.ptr(g), _lib.ptr(slab_wt),
                                                           _lib.ptr(dx)), "glow_rows_conv_backward_data")
             if ctx.needs_input_grad[1]:
-                xm, dym = x * tr.valid, dy * tr.valid          # the reduction runs over real rows only
+                xm = x if ctx.x_masked else x * tr.valid          # the reduction runs over real rows only
                 dwt = torch.empty((taps, cin, cout), dtype=torch.float32, device=dev)
                 db = torch.empty(cout, dtype=torch.float32, device=dev) if ctx.has_bias else None
-                _lib.check(L.glow_rows_conv_backward_weight(ctypes.byref(call), _lib.ptr(xm), _lib.ptr(dym),
+                _lib.check(L.glow_rows_conv_backward_weight(ctypes.byref(call), _lib.ptr(xm), _lib.ptr(g),
                                                             _lib.ptr(dwt), _lib.ptr(db)),
                            "glow_rows_conv_backward_weight")
                 dw = dwt.permute(2, 1, 0)
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None, None
 
 
-def rows_conv(x, conv, tr):
-    """Apply a torch.nn.Conv1d's parameters to packed rows."""
-    return RowsConvFn.apply(x, conv.weight, conv.bias, tr)
+def rows_conv(x, conv, tr, relu=False, p=0.0, seed=0, x_masked=False):
+    """Apply a torch.nn.Conv1d's parameters to packed rows.  x_masked: the caller guarantees x is zero on
+    guard rows (every op of this module writes them as zeros), which saves a masking pass in backward."""
+    return _RowsConvApply.apply(x, conv.weight, conv.bias, tr, relu, p, seed, x_masked)
+
+
+class _RowsConvApply(RowsConvFn):
+    @staticmethod
+    def forward(ctx, x, weight, bias, tr, relu, p, seed, x_masked):
+        ctx.x_masked = bool(x_masked)
+        return RowsConvFn.forward(ctx, x, weight, bias, tr, relu, p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return RowsConvFn.backward(ctx, dy) + (None,)
+
+
+class RowsNormFn(torch.autograd.Function):
+    """y = mask * Dropout_out(ReLU?(LayerNorm(Dropout_in(a) + b))) on packed rows (csrc/rows_norm.cu)."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, tr, eps, p_in, seed_in, relu, p_out, seed_out):
+        dev = a.device
+        a = a.contiguous().float()
+        b = b.contiguous().float() if b is not None else None
+        if not (p_in > 0 and seed_in):
+            p_in, seed_in = 0.0, 0
+        if not (p_out > 0 and seed_out):
+            p_out, seed_out = 0.0, 0
+        c = _lib.RowsNormCall()
+        c.rows_pad, c.channels, c.row_utt, c.eps = tr.rows_pad, a.shape[1], tr.rm.row_utt.data_ptr(), float(eps)
+        c.p_in, c.seed_in = float(p_in), int(seed_in) & 0xFFFFFFFFFFFFFFFF
+        c.relu, c.p_out, c.seed_out = int(bool(relu)), float(p_out), int(seed_out) & 0xFFFFFFFFFFFFFFFF
+        c.step_dev = _lib.step_counter_ptr(dev) if (seed_in or seed_out) else None
+        s = torch.empty_like(a)
+        y = torch.empty_like(a)
+        stats = torch.empty((tr.rows_pad, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            c.stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().glow_rows_norm_forward(ctypes.byref(c), _lib.ptr(a), _lib.ptr(b),
+                                                         _lib.ptr(gamma.detach().contiguous()),
+                                                         _lib.ptr(beta.detach().contiguous()),
+                                                         _lib.ptr(s), _lib.ptr(stats), _lib.ptr(y)),
+                       "glow_rows_norm_forward")
+        ctx.call, ctx.has_b = c, b is not None
+        ctx.save_for_backward(s, stats, y, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, stats, y, gamma = ctx.saved_tensors
+        c, dev = ctx.call, dy.device
+        dy = dy.contiguous().float()
+        da = torch.empty_like(dy)
+        db = torch.empty_like(dy) if (ctx.has_b and c.seed_in) else None     # without input dropout d b == d a
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        with torch.cuda.device(dev):
+            c.stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().glow_rows_norm_backward(ctypes.byref(c), _lib.ptr(dy), _lib.ptr(y), _lib.ptr(s),
+                                                          _lib.ptr(stats), _lib.ptr(gamma.detach().contiguous()),
+                                                          _lib.ptr(da), _lib.ptr(db), _lib.ptr(dgamma),
+                                                          _lib.ptr(dbeta)), "glow_rows_norm_backward")
+        if ctx.has_b and db is None:
+            db = da
+        return da, (db if ctx.has_b else None), dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def rows_norm(a, b, ln, tr, p_in=0.0, seed_in=0, relu=False, p_out=0.0, seed_out=0):
+    """Apply a torch.nn.LayerNorm's parameters: mask * Dropout_out(ReLU?(LN(Dropout_in(a) + b)))."""
+    return RowsNormFn.apply(a, b, ln.weight, ln.bias, tr, ln.eps, p_in, seed_in, relu, p_out, seed_out)

@@ -107,12 +107,13 @@ class RPR_Multihead_Attention(torch.nn.Module):
         GEMMs over the rows, the attention core on [B, C, T] views of their outputs."""
         from . import rows as _rows
         d = self.layer_Dict
-        q, k, v = (tr.unpack(_rows.rows_conv(x, d[n], tr)).transpose(1, 2) for n in ("Query", "Key", "Value"))
+        q, k, v = (tr.unpack(_rows.rows_conv(x, d[n], tr, x_masked=True)).transpose(1, 2)
+                   for n in ("Query", "Key", "Value"))
         seed = self._next_seed()
         lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
         out, _ = _AttnCoreFn.apply(q, k, v, self.weight_K, self.weight_V, lengths, None, self.num_heads,
                                    self.relative_postion_clipping_distance, self.dropout_rate, seed, False)
-        return _rows.rows_conv(tr.pack(out.transpose(1, 2)), d["Projection"], tr)
+        return _rows.rows_conv(tr.pack(out.transpose(1, 2)), d["Projection"], tr, x_masked=True)
 
     def _next_seed(self):
         if not (self.training and self.dropout_rate > 0):

@@ -226,6 +226,10 @@ typedef struct {
     int cin, cout, taps;
     int rows_pad;
     const int32_t *row_utt;
+    int   relu;                 /* forward only: ReLU on the output (Modules.py:568) */
+    float p_out;                /* forward only: dropout on the output when seed_out != 0 (Modules.py:568,570) */
+    uint64_t seed_out;
+    const uint64_t *step_dev;   /* optional device step counter mixed into seed_out, or NULL */
     glow_stream_t stream;
 } glow_rows_conv_call;
 
@@ -234,7 +238,7 @@ size_t glow_rows_conv_slab_elems(int cin, int cout, int taps);
 /* weight [cout, cin, taps] fp32 (torch Conv1d layout) -> slab_w (forward operand) and slab_wt
  * (data-gradient operand), each glow_rows_conv_slab_elems bf16 elements. */
 int glow_rows_conv_pack(const glow_rows_conv_call *call, const float *weight, void *slab_w, void *slab_wt);
-/* y = mask * (bias + conv(mask * x)); bias may be NULL. */
+/* y = mask * Dropout(ReLU?(bias + conv(mask * x))); bias may be NULL. */
 int glow_rows_conv_forward(const glow_rows_conv_call *call, const float *x, const void *slab_w,
                            const float *bias, float *y);
 /* dx = mask * conv^T(mask * dy). */
@@ -244,6 +248,37 @@ int glow_rows_conv_backward_data(const glow_rows_conv_call *call, const float *d
  * of dy (overwritten; may be NULL).  x and dy must already be zero on guard rows. */
 int glow_rows_conv_backward_weight(const glow_rows_conv_call *call, const float *x, const float *dy,
                                    float *dw, float *dbias);
+
+/* Gradient through the activation glow_rows_conv_forward fused on its output f [rows_pad, width]:
+ * g = mask * dy * (relu ? [f != 0] : keep(row, col)) / (1 - p)   (f may be NULL when relu == 0). */
+int glow_rows_act_backward(const int32_t *row_utt, int rows_pad, int width, int relu, float p,
+                           uint64_t seed, const uint64_t *step_dev, const float *dy, const float *f,
+                           float *g, glow_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Fused LayerNorm over packed token rows
+ * replaces: LayerNorm -> ReLU -> Dropout of CLRD (Modules.py:485-487) and
+ *           LayerNorm_0(Dropout(attention) + x) / LayerNorm_1(Dropout(conv) + y) of
+ *           ANCRDCN (Modules.py:563-566, 571-573), with their backward:
+ *   y = mask * Dropout_out(ReLU?(gamma * norm(Dropout_in(a) + b) + beta))
+ * a, b (nullable), y are fp32 [rows_pad, 192]; s (the pre-norm sum) and stats [rows_pad, 2]
+ * (mean, rstd) are saved for the backward.  dgamma / dbeta are overwritten.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int rows_pad, channels;     /* channels must be 192 */
+    const int32_t *row_utt;
+    float eps;
+    float p_in;   uint64_t seed_in;    /* dropout on `a` (0 / seed 0: none) */
+    int   relu;
+    float p_out;  uint64_t seed_out;   /* dropout on the output (only together with relu) */
+    const uint64_t *step_dev;
+    glow_stream_t stream;
+} glow_rows_norm_call;
+int glow_rows_norm_forward(const glow_rows_norm_call *call, const float *a, const float *b,
+                           const float *gamma, const float *beta, float *s, float *stats, float *y);
+int glow_rows_norm_backward(const glow_rows_norm_call *call, const float *dy, const float *y,
+                            const float *s, const float *stats, const float *gamma,
+                            float *da, float *db, float *dgamma, float *dbeta);
 
 /* ------------------------------------------------------------------------ *
  * Optimizer step over the flat parameter / gradient buffers

@@ -47,6 +47,71 @@ def test_rows_conv_matches_conv1d(cin, cout, taps):
     assert rel(conv.bias.grad, want_db) < 2e-2
 
 
+@pytest.mark.parametrize("relu,with_b", [(False, True), (True, False)])
+def test_rows_norm_matches_layernorm(relu, with_b):
+    """Eval mode (no dropout): mask * ReLU?(LayerNorm(a + b)) and its gradients, fp32 both ways: 1e-4."""
+    from glow_tts_b200 import rows
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    tr = rows.token_rows([37, 5, 64, 1, 23], 64, dev)
+    ln = torch.nn.LayerNorm(192, eps=1e-4).to(dev)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(192, device=dev)); ln.bias.copy_(torch.randn(192, device=dev))
+    a0 = torch.randn(tr.rows_pad, 192, device=dev)
+    b0 = torch.randn(tr.rows_pad, 192, device=dev) if with_b else None
+    g = torch.randn(tr.rows_pad, 192, device=dev)
+    res = []
+    for path in ("torch", "native"):
+        ln.weight.grad = ln.bias.grad = None
+        a = a0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if with_b else None
+        if path == "torch":
+            y = ln(a + b if with_b else a)
+            y = (F.relu(y) if relu else y) * tr.valid
+        else:
+            y = rows.rows_norm(a, b, ln, tr, relu=relu)
+        y.backward(g)
+        res.append((y.detach(), a.grad * tr.valid, (b.grad * tr.valid) if with_b else None, ln.weight.grad.clone(),
+                    ln.bias.grad.clone()))
+    for got, want in zip(res[1], res[0]):
+        if want is not None:
+            assert rel(got, want) < 1e-4
+
+
+def test_rows_dropout_forward_backward_agree():
+    """Training mode: the masks the forward kernels draw are the ones their backward replays: with an
+    all-ones upstream gradient, d(sum y)/dx from autograd must equal a central finite difference."""
+    from glow_tts_b200 import rows
+    torch.manual_seed(9)
+    dev = torch.device("cuda:0")
+    tr = rows.token_rows([20, 9], 20, dev)
+    ln = torch.nn.LayerNorm(192, eps=1e-4).to(dev)
+    a = (torch.randn(tr.rows_pad, 192, device=dev) * tr.valid).requires_grad_(True)
+    b = (torch.randn(tr.rows_pad, 192, device=dev) * tr.valid)
+    y = rows.rows_norm(a, b, ln, tr, p_in=0.3, seed_in=1234, relu=True, p_out=0.5, seed_out=99)
+    frac = float((y[tr.valid[:, 0] > 0] == 0).float().mean())
+    assert 0.55 < frac < 0.95                                   # ReLU (about half) and dropout 0.5 both zero outputs
+    y.sum().backward()
+    r, c, eps = int(tr.rm.utt_off[0]) + 3, 17, 1e-2
+    with torch.no_grad():
+        ap, am = a.detach().clone(), a.detach().clone()
+        ap[r, c] += eps; am[r, c] -= eps
+        fd = (rows.rows_norm(ap, b, ln, tr, p_in=0.3, seed_in=1234, relu=True, p_out=0.5, seed_out=99).sum()
+              - rows.rows_norm(am, b, ln, tr, p_in=0.3, seed_in=1234, relu=True, p_out=0.5, seed_out=99).sum()) / (2 * eps)
+    assert abs(float(fd) - float(a.grad[r, c])) < 5e-2 * max(1.0, abs(float(fd)))
+    # conv with fused ReLU + dropout: same masks in backward
+    conv = torch.nn.Conv1d(192, 768, 3, padding=1).to(dev)
+    x = (torch.randn(tr.rows_pad, 192, device=dev) * tr.valid).requires_grad_(True)
+    f = rows.rows_conv(x, conv, tr, relu=True, p=0.4, seed=77, x_masked=True)
+    f.sum().backward()
+    with torch.no_grad():
+        f2 = rows.rows_conv(x.detach(), conv, tr, relu=True, p=0.4, seed=77)
+        assert torch.equal(f.detach(), f2)                       # the mask is a pure function of (seed, row, column)
+        keep = (f2 != 0).float()                                 # d(sum f)/d(conv out) = keep / (1 - p)
+        want_db = (keep / 0.6).sum(0)
+    assert rel(conv.bias.grad, want_db) < 1e-3
+
+
 @pytest.mark.parametrize("name", ["vanilla_small", "se_small"])
 def test_rows_encoder_matches_torch_encoder(name):
     from tests._model_util import load_case

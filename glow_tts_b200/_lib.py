@@ -34,7 +34,7 @@ class FlowCall(ctypes.Structure):            # glow_flow_call
 class AttnCall(ctypes.Structure):            # glow_attn_call
     _fields_ = [("q", _P), ("k", _P), ("v", _P), ("wk", _P), ("wv", _P), ("lengths", _P), ("mask", _P),
                 ("batch", _I), ("heads", _I), ("t", _I), ("head_dim", _I), ("window", _I),
-                ("dropout", _F), ("seed", _U64), ("step_dev", _P), ("stream", _P)]
+                ("dropout", _F), ("seed", _U64), ("step_dev", _P), ("utt_off", _P), ("ld", _I), ("stream", _P)]
 
 
 class RowsConvCall(ctypes.Structure):        # glow_rows_conv_call

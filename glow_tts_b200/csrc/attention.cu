@@ -41,6 +41,8 @@ struct AttnArgs {
     float scale, drop_p;
     uint64_t seed;                 // 0: no dropout
     const uint64_t *step_dev;      // optional device step counter mixed into seed (CUDA-graph replays)
+    const int32_t *utt_off;        // rows mode (non-null): q/k/v/out and their gradients are packed token rows
+    int ld;                        //   [rows, ld], element (b, h, d, t) at (utt_off[b] + t) * ld + h*d_head + d
     // forward outputs
     float *out;                    // [B, H*d, T]
     float *probs;                  // [B,H,T,T] softmax before dropout (saved for backward) or null
@@ -59,10 +61,23 @@ __device__ __forceinline__ uint64_t attn_seed(const AttnArgs &a)
     return (a.seed ^ (__ldg(a.step_dev) * 0xD6E8FEB86659FD93ull)) | 1ull;
 }
 
-// tile[i][e] <- src[b, h*d + e, i0 + i]   (coalesced along time); rows beyond T read 0
-__device__ __forceinline__ void load_tile_T(float (*tile)[kAD + 1], const float *src, int b, int h, int H, int T,
+// tile[i][e] <- src(b, h, e, i0 + i); positions beyond the sequence read 0.
+//   [B, H*d, T] layout: coalesced along time.  Rows layout (a.utt_off != null): the sentence's rows are
+//   contiguous, 96 floats of one head per row -> coalesced along the channel.
+__device__ __forceinline__ void load_tile_T(float (*tile)[kAD + 1], const float *src, const AttnArgs &a, int b, int h,
                                             int i0, int tid)
 {
+    if (a.utt_off != nullptr) {
+        const int len = a.lengths[b];
+        const float *base = src + (size_t)a.utt_off[b] * a.ld + h * kAD;
+        for (int e = tid; e < kAD * kAQ; e += kAThreads) {
+            const int i = e / kAD, d = e - i * kAD;
+            const int t = i0 + i;
+            tile[i][d] = (t < len) ? base[(size_t)t * a.ld + d] : 0.f;
+        }
+        return;
+    }
+    const int T = a.T, H = a.H;
     for (int e = tid; e < kAD * kAQ; e += kAThreads) {
         const int d = e >> 5, i = e & 31;
         const int t = i0 + i;
@@ -70,10 +85,21 @@ __device__ __forceinline__ void load_tile_T(float (*tile)[kAD + 1], const float 
     }
 }
 
-// dst[b, h*d + e, i0 + i] <- tile[i][e]
-__device__ __forceinline__ void store_tile_T(const float (*tile)[kAD + 1], float *dst, int b, int h, int H, int T,
+// dst(b, h, e, i0 + i) <- tile[i][e]
+__device__ __forceinline__ void store_tile_T(const float (*tile)[kAD + 1], float *dst, const AttnArgs &a, int b, int h,
                                              int i0, int tid)
 {
+    if (a.utt_off != nullptr) {
+        const int len = a.lengths[b];
+        float *base = dst + (size_t)a.utt_off[b] * a.ld + h * kAD;
+        for (int e = tid; e < kAD * kAQ; e += kAThreads) {
+            const int i = e / kAD, d = e - i * kAD;
+            const int t = i0 + i;
+            if (t < len) base[(size_t)t * a.ld + d] = tile[i][d];
+        }
+        return;
+    }
+    const int T = a.T, H = a.H;
     for (int e = tid; e < kAD * kAQ; e += kAThreads) {
         const int d = e >> 5, i = e & 31;
         const int t = i0 + i;
@@ -84,8 +110,8 @@ __device__ __forceinline__ void store_tile_T(const float (*tile)[kAD + 1], float
 // S[i][j] = A_i . B_j + [|j-i|<=w] A_i . rel[j-i+w]   for the CTA's 32 rows, all j < T
 //   A tile in As, B streamed from `bsrc` ([B,H*d,T]) in 32-row chunks through Bs.
 __device__ __forceinline__ void band_scores(float (*As)[kAD + 1], float (*Bs)[kAD + 1], const float *rel_s,
-                                            float *S, int Tp, const float *bsrc, int b, int h, int H, int T, int i0,
-                                            int window, int tid, float (*AR)[kAMaxRel + 1])
+                                            float *S, int Tp, const float *bsrc, const AttnArgs &a, int b, int h, int T,
+                                            int i0, int window, int tid, float (*AR)[kAMaxRel + 1])
 {
     const int nrel = 2 * window + 1;
     // AR[i][r] = A_i . rel[r]
@@ -98,7 +124,7 @@ __device__ __forceinline__ void band_scores(float (*As)[kAD + 1], float (*Bs)[kA
     const int i = tid >> 3, jq = (tid & 7) * 4;
     for (int j0 = 0; j0 < T; j0 += 32) {
         __syncthreads();
-        load_tile_T(Bs, bsrc, b, h, H, T, j0, tid);
+        load_tile_T(Bs, bsrc, a, b, h, j0, tid);
         __syncthreads();
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int d = 0; d < kAD; ++d) {
@@ -122,7 +148,7 @@ __device__ __forceinline__ void band_scores(float (*As)[kAD + 1], float (*Bs)[kA
 
 // O[i][e] = sum_j S[i][j] * B_j[e] + sum_r S[i][i+r-w] * rel[r][e]  -> Os (32 x 96)
 __device__ __forceinline__ void band_apply(const float *S, int Tp, float (*Bs)[kAD + 1], const float *rel_s,
-                                           float (*Os)[kAD + 1], const float *bsrc, int b, int h, int H, int T,
+                                           float (*Os)[kAD + 1], const float *bsrc, const AttnArgs &a, int b, int h, int T,
                                            int i0, int window, int tid)
 {
     const int i = tid >> 3, e0 = tid & 7;
@@ -131,7 +157,7 @@ __device__ __forceinline__ void band_apply(const float *S, int Tp, float (*Bs)[k
     for (int m = 0; m < 12; ++m) acc[m] = 0.f;
     for (int j0 = 0; j0 < T; j0 += 32) {
         __syncthreads();
-        load_tile_T(Bs, bsrc, b, h, H, T, j0, tid);
+        load_tile_T(Bs, bsrc, a, b, h, j0, tid);
         __syncthreads();
         const int jn = min(32, T - j0);
         for (int j = 0; j < jn; ++j) {
@@ -197,10 +223,11 @@ rpr_attn_fwd_kernel(const AttnArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
     const int T = a.T, nrel = 2 * a.window + 1;
-    load_tile_T(sm.As, a.q, b, h, a.H, T, i0, tid);
+    if (a.utt_off != nullptr && i0 >= a.lengths[b]) return;      // rows layout: a tile of pure padding has no rows
+    load_tile_T(sm.As, a.q, a, b, h, i0, tid);
     for (int e = tid; e < nrel * kAD; e += kAThreads) sm.rel[e] = a.wk[e];
     __syncthreads();
-    band_scores(sm.As, sm.Bs, sm.rel, sm.S, sm.Tp, a.k, b, h, a.H, T, i0, a.window, tid, sm.AR);
+    band_scores(sm.As, sm.Bs, sm.rel, sm.S, sm.Tp, a.k, a, b, h, T, i0, a.window, tid, sm.AR);
     // softmax (+ dropout) per row: warp w owns rows 4w .. 4w+3
     for (int rr = 0; rr < 4; ++rr) {
         const int i = warp * 4 + rr, gi = i0 + i;
@@ -231,8 +258,8 @@ rpr_attn_fwd_kernel(const AttnArgs a)
     }
     __syncthreads();
     for (int e = tid; e < nrel * kAD; e += kAThreads) sm.rel[e] = a.wv[e];
-    band_apply(sm.S, sm.Tp, sm.Bs, sm.rel, sm.As, a.v, b, h, a.H, T, i0, a.window, tid);
-    store_tile_T(sm.As, a.out, b, h, a.H, T, i0, tid);
+    band_apply(sm.S, sm.Tp, sm.Bs, sm.rel, sm.As, a.v, a, b, h, T, i0, a.window, tid);
+    store_tile_T(sm.As, a.out, a, b, h, i0, tid);
 }
 
 // Backward, query-tile kernel: dPd -> dS (scaled) -> dQ, dwK, dwV; writes ds scratch.
@@ -246,11 +273,12 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
     const int i0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
     const int T = a.T, nrel = 2 * a.window + 1;
     const float inv_keep = 1.f / (1.f - a.drop_p);
+    if (a.utt_off != nullptr && i0 >= a.lengths[b]) return;
     // dPd[i][j] = dO_i . v_j + [band] dO_i . wV[j-i+w]
-    load_tile_T(sm.As, a.dout, b, h, a.H, T, i0, tid);
+    load_tile_T(sm.As, a.dout, a, b, h, i0, tid);
     for (int e = tid; e < nrel * kAD; e += kAThreads) sm.rel[e] = a.wv[e];
     __syncthreads();
-    band_scores(sm.As, sm.Bs, sm.rel, sm.S, sm.Tp, a.v, b, h, a.H, T, i0, a.window, tid, sm.AR);
+    band_scores(sm.As, sm.Bs, sm.rel, sm.S, sm.Tp, a.v, a, b, h, T, i0, a.window, tid, sm.AR);
     // dwV[r][e] += sum_i Pd[i][i+r-w] * dO[i][e]   (As still holds dO)
     for (int e = tid; e < nrel * kAD; e += kAThreads) {
         const int r = e / kAD, d = e % kAD;
@@ -289,7 +317,7 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
     }
     __syncthreads();
     // dwK[r][e] += sum_i dSs[i][i+r-w] * q[i][e]  ; dQ = dSs K + band wK
-    load_tile_T(sm.As, a.q, b, h, a.H, T, i0, tid);
+    load_tile_T(sm.As, a.q, a, b, h, i0, tid);
     for (int e = tid; e < nrel * kAD; e += kAThreads) sm.rel[e] = a.wk[e];
     __syncthreads();
     for (int e = tid; e < nrel * kAD; e += kAThreads) {
@@ -301,8 +329,8 @@ rpr_attn_bwd_q_kernel(const AttnArgs a)
         }
         atomicAdd(a.dwk + e, acc);
     }
-    band_apply(sm.S, sm.Tp, sm.Bs, sm.rel, sm.As, a.k, b, h, a.H, T, i0, a.window, tid);
-    store_tile_T(sm.As, a.dq, b, h, a.H, T, i0, tid);
+    band_apply(sm.S, sm.Tp, sm.Bs, sm.rel, sm.As, a.k, a, b, h, T, i0, a.window, tid);
+    store_tile_T(sm.As, a.dq, a, b, h, i0, tid);
 }
 
 // Backward, key-tile kernel: dV[j] = sum_i Pd[i][j] dO_i ; dK[j] = sum_i dSs[i][j] q_i
@@ -315,15 +343,17 @@ rpr_attn_bwd_kv_kernel(const AttnArgs a)
     const int tid = threadIdx.x;
     const int j0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
     const int T = a.T;
+    const int Tb = (a.utt_off != nullptr) ? min(a.T, a.lengths[b]) : a.T;    // rows layout: queries beyond the sentence add 0
     const float inv_keep = 1.f / (1.f - a.drop_p);
+    if (a.utt_off != nullptr && j0 >= a.lengths[b]) return;
     const int j = tid >> 3, e0 = tid & 7;
     float accv[12], acck[12];
 #pragma unroll
     for (int m = 0; m < 12; ++m) { accv[m] = 0.f; acck[m] = 0.f; }
-    for (int i0 = 0; i0 < T; i0 += kAQ) {
+    for (int i0 = 0; i0 < Tb; i0 += kAQ) {
         __syncthreads();
-        load_tile_T(Qs, a.q, b, h, a.H, T, i0, tid);
-        load_tile_T(Ds, a.dout, b, h, a.H, T, i0, tid);
+        load_tile_T(Qs, a.q, a, b, h, i0, tid);
+        load_tile_T(Ds, a.dout, a, b, h, i0, tid);
         for (int e = tid; e < kAQ * kAQ; e += kAThreads) {
             const int i = e >> 5, jj = e & 31;
             const int gi = i0 + i, gj = j0 + jj;
@@ -351,8 +381,8 @@ rpr_attn_bwd_kv_kernel(const AttnArgs a)
 #pragma unroll
     for (int m = 0; m < 12; ++m) { Ds[j][e0 + 8 * m] = accv[m]; Qs[j][e0 + 8 * m] = acck[m]; }
     __syncthreads();
-    store_tile_T(Ds, a.dv, b, h, a.H, T, j0, tid);
-    store_tile_T(Qs, a.dk, b, h, a.H, T, j0, tid);
+    store_tile_T(Ds, a.dv, a, b, h, j0, tid);
+    store_tile_T(Qs, a.dk, a, b, h, j0, tid);
 }
 
 static int check_attn(const glow_attn_call *c)
@@ -366,6 +396,8 @@ static int check_attn(const glow_attn_call *c)
     GLOW_REQUIRE(c->t <= 512, GLOW_ERR_UNSUPPORTED, "attention: t=%d > 512", c->t);
     GLOW_REQUIRE(c->dropout >= 0.f && c->dropout < 1.f, GLOW_ERR_INVALID, "attention: dropout=%f", c->dropout);
     GLOW_REQUIRE(c->q && c->k && c->v && c->wk && c->wv, GLOW_ERR_INVALID, "attention: null q/k/v/wk/wv");
+    GLOW_REQUIRE(c->utt_off == nullptr || (c->lengths != nullptr && c->ld >= c->heads * c->head_dim), GLOW_ERR_INVALID,
+                 "attention: rows layout needs lengths and ld >= heads*head_dim (ld=%d)", c->ld);
     return GLOW_OK;
 }
 
@@ -379,6 +411,7 @@ static AttnArgs to_args(const glow_attn_call *c)
     a.drop_p = c->dropout;
     a.seed = c->dropout > 0.f ? c->seed : 0;
     a.step_dev = a.seed != 0 ? c->step_dev : nullptr;
+    a.utt_off = c->utt_off; a.ld = c->ld;
     return a;
 }
 

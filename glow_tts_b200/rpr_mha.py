@@ -72,6 +72,50 @@ class _AttnCoreFn(torch.autograd.Function):
                 None, None, None, None, None, None, None)
 
 
+class _AttnRowsFn(torch.autograd.Function):
+    """The same core on packed token rows: q, k, v, out are [rows, heads*d] (glow_attn_call.utt_off / ld)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, wk, wv, tr, lengths, heads, window, dropout, seed):
+        rows, c = q.shape
+        d = c // heads
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        wk2, wv2 = wk.reshape(-1, d).contiguous().float(), wv.reshape(-1, d).contiguous().float()
+        dev = q.device
+        call = _lib.AttnCall()
+        call.q, call.k, call.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+        call.wk, call.wv = wk2.data_ptr(), wv2.data_ptr()
+        call.lengths, call.mask = lengths.data_ptr(), None
+        call.batch, call.heads, call.t, call.head_dim, call.window = tr.batch, heads, tr.t_max, d, window
+        call.dropout, call.seed = float(dropout), int(seed)
+        call.step_dev = _lib.step_counter_ptr(dev) if seed else None
+        call.utt_off, call.ld = tr.rm.utt_off.data_ptr(), c
+        out = torch.zeros_like(q)                                   # guard rows stay zero
+        probs = torch.empty((tr.batch, heads, tr.t_max, tr.t_max), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call.stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.lib().glow_rpr_attention_forward(ctypes.byref(call), _lib.ptr(out), _lib.ptr(probs), None)
+        _lib.check(rc, "glow_rpr_attention_forward")
+        ctx.call, ctx.keep, ctx.wshape = call, (q, k, v, wk2, wv2, lengths, probs, tr), wk.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, wk2, wv2, lengths, probs, tr = ctx.keep
+        call, dev = ctx.call, q.device
+        dout = dout.contiguous().float()
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        dwk, dwv = torch.empty_like(wk2), torch.empty_like(wv2)
+        ds = torch.empty_like(probs)
+        with torch.cuda.device(dev):
+            call.stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.lib().glow_rpr_attention_backward(
+                ctypes.byref(call), _lib.ptr(dout), _lib.ptr(probs), _lib.ptr(ds),
+                _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), _lib.ptr(dwk), _lib.ptr(dwv))
+        _lib.check(rc, "glow_rpr_attention_backward")
+        return dq, dk, dv, dwk.view(ctx.wshape), dwv.view(ctx.wshape), None, None, None, None, None, None
+
+
 class RPR_Multihead_Attention(torch.nn.Module):
     def __init__(self, query_channels, calc_channels, out_channels, num_heads,
                  relative_postion_clipping_distance=None, share_relative_postion_weight=True,
@@ -107,13 +151,12 @@ class RPR_Multihead_Attention(torch.nn.Module):
         GEMMs over the rows, the attention core on [B, C, T] views of their outputs."""
         from . import rows as _rows
         d = self.layer_Dict
-        q, k, v = (tr.unpack(_rows.rows_conv(x, d[n], tr, x_masked=True)).transpose(1, 2)
-                   for n in ("Query", "Key", "Value"))
+        q, k, v = (_rows.rows_conv(x, d[n], tr, x_masked=True) for n in ("Query", "Key", "Value"))
         seed = self._next_seed()
         lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
-        out, _ = _AttnCoreFn.apply(q, k, v, self.weight_K, self.weight_V, lengths, None, self.num_heads,
-                                   self.relative_postion_clipping_distance, self.dropout_rate, seed, False)
-        return _rows.rows_conv(tr.pack(out.transpose(1, 2)), d["Projection"], tr, x_masked=True)
+        out = _AttnRowsFn.apply(q, k, v, self.weight_K, self.weight_V, tr, lengths, self.num_heads,
+                                self.relative_postion_clipping_distance, self.dropout_rate, seed)
+        return _rows.rows_conv(out, d["Projection"], tr, x_masked=True)
 
     def _next_seed(self):
         if not (self.training and self.dropout_rate > 0):

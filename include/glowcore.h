@@ -197,6 +197,11 @@ typedef struct {
     float dropout;              /* on the probabilities, only when seed != 0 */
     uint64_t seed;
     const uint64_t *step_dev;   /* optional device step counter mixed into `seed` (CUDA-graph replays), or NULL */
+    const int32_t *utt_off;     /* NULL: q/k/v/out are [batch, heads*head_dim, t].  Else ROWS layout: they (and the
+                                   gradients of glow_rpr_attention_backward) are packed token rows [rows, ld] with
+                                   sentence b on rows utt_off[b] .. utt_off[b]+lengths[b]-1 and head h on columns
+                                   h*head_dim .. ; `lengths` is then required; rows of other sentences are never touched */
+    int   ld;
     glow_stream_t stream;
 } glow_attn_call;
 

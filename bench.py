@@ -361,8 +361,7 @@ def run_own(args):
     barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, graphed)
         return 0
 
     pk = peaks()
@@ -420,9 +419,21 @@ def run_own(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world, graphed)
     return 0
+
+
+def _finish(world, graphed):
+    """Leave without tearing NCCL down: destroy_process_group() after a CUDA graph that captured an
+    all-reduce has been seen to hang for minutes; every collective is complete here (the barrier
+    above), so the ranks just flush and exit."""
+    if world <= 1:
+        return
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

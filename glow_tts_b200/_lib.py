@@ -80,6 +80,8 @@ SIGNATURES = {
     "glow_rows_conv_forward": (_I, [_PROWS, _P, _P, _P, _P]),
     "glow_rows_conv_backward_data": (_I, [_PROWS, _P, _P, _P]),
     "glow_rows_conv_backward_weight": (_I, [_PROWS, _P, _P, _P, _P]),
+    "glow_rows_conv_backward_weight_accum": (_I, [_PROWS, _P, _P, _P, _P, _P]),
+    "glow_side_join": (_I, [_P]),
     "glow_rows_act_backward": (_I, [_P, _I, _I, _I, _F, _U64, _P, _P, _P, _P, _P]),
     "glow_rows_norm_forward": (_I, [_PNORM, _P, _P, _P, _P, _P, _P, _P]),
     "glow_rows_norm_backward": (_I, [_PNORM, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -172,6 +174,12 @@ def device_ints(values, dtype, device):
             _DEV_INTS.clear()
         t = _DEV_INTS[key] = torch.tensor(list(key[0]), dtype=dtype).to(device)
     return t
+
+
+def side_join(device):
+    """Make the current stream wait for everything libglowcore forked to its side stream (encoder wgrads)."""
+    with torch.cuda.device(device):
+        check(lib().glow_side_join(stream_ptr(device)), "glow_side_join")
 
 
 def launch_count():

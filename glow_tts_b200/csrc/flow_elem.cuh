@@ -245,6 +245,44 @@ colsum_kernel(const T *__restrict__ D, int ld, int rows, int N, float *__restric
     }
 }
 
+// All bias gradients of one block in ONE launch: job j sums the columns of src_j [rows, n_j] and adds the
+// result to up to four destinations (d(out) feeds the skip half of three Res_Skip biases and the whole
+// fourth).  grid = (row chunks of 128, jobs), 192 threads, each owning two adjacent columns (4 B / 8 B
+// loads, a row is read as one contiguous run).
+constexpr int kMaxColsumJobs = 12;
+template <typename T>
+struct ColsumJobs {
+    int count;
+    const T *src[kMaxColsumJobs];
+    int n[kMaxColsumJobs];
+    float *dst[kMaxColsumJobs][4];
+};
+template <typename T>
+static __global__ void __launch_bounds__(192)
+colsum_multi_kernel(const __grid_constant__ ColsumJobs<T> jobs, int rows)
+{
+    const int j = blockIdx.y, n = jobs.n[j], c2 = threadIdx.x;
+    if (2 * c2 >= n) return;
+    const T *src = jobs.src[j];
+    const int r0 = blockIdx.x * 128, r1 = min(rows, r0 + 128);
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+        if constexpr (sizeof(T) == 2) {
+            float x, y;
+            unpack_bf16x2(reinterpret_cast<const uint32_t *>(src + (size_t)r * n)[c2], x, y);
+            a0 += x; a1 += y;
+        } else {
+            const float2 v = reinterpret_cast<const float2 *>(src + (size_t)r * n)[c2];
+            a0 += v.x; a1 += v.y;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        float *dst = jobs.dst[j][d];
+        if (dst != nullptr) { atomicAdd(dst + 2 * c2, a0); atomicAdd(dst + 2 * c2 + 1, a1); }
+    }
+}
+
 // Per-utterance column sums: out[b][n] = sum_{rows of b} D[row, n]  (speaker-bias gradient).
 // grid = (ceil(N/128), B), 128 threads.
 template <typename T>

@@ -261,10 +261,8 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         // ---- weight / bias gradients of this block (side stream)
         GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
         GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
-        // dW_end[192][160] = OUT^T DOUTS ; db_end
+        // dW_end[192][160] = OUT^T DOUTS
         GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f));
-        colsum_kernel<ActT><<<dim3(kC / 32, 32), 256, 0, side>>>(DOUTS, kC, R, kC, dwp + c.bp.end_b);
-        GLOW_CHECK_LAUNCH("colsum_kernel");
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
             const int rs_n = last ? kH : kG;
@@ -272,28 +270,33 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             if (!last) {
                 GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DH[i + 1], kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
                 GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f));
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DH[i + 1], kH, R, kH, dwp + c.bp.rs_b[i]);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i] + kH);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
             } else {
                 GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f));
-                colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DOUT, kH, R, kH, dwp + c.bp.rs_b[i]);
-                GLOW_CHECK_LAUNCH("colsum_kernel");
             }
             // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
             GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
                                 kTaps, kH, (long long)kH * kG, 0.f));
-            colsum_kernel<ActT><<<dim3(kG / 32, 32), 256, 0, side>>>(DPRE[i], kG, R, kG, dwp + c.bp.in_b[i]);
-            GLOW_CHECK_LAUNCH("colsum_kernel");
         }
         if (kBf16) {
             GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
         } else {
             GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f));
         }
-        colsum_kernel<ActT><<<dim3(kH / 32, 32), 256, 0, side>>>(DH[0], kH, R, kH, dwp + c.bp.start_b);
-        GLOW_CHECK_LAUNCH("colsum_kernel");
+        {   // every bias gradient of the block: column sums of the gradients the GEMMs above read (one launch)
+            ColsumJobs<ActT> cj{};
+            auto add = [&](const ActT *src, int n, float *d0, float *d1 = nullptr, float *d2 = nullptr, float *d3 = nullptr) {
+                cj.src[cj.count] = src; cj.n[cj.count] = n;
+                cj.dst[cj.count][0] = d0; cj.dst[cj.count][1] = d1; cj.dst[cj.count][2] = d2; cj.dst[cj.count][3] = d3;
+                ++cj.count;
+            };
+            add(DOUTS, kC, dwp + c.bp.end_b);
+            add(DOUT, kH, dwp + c.bp.rs_b[0] + kH, dwp + c.bp.rs_b[1] + kH, dwp + c.bp.rs_b[2] + kH, dwp + c.bp.rs_b[3]);
+            for (int i = 0; i < kLayers - 1; ++i) add(DH[i + 1], kH, dwp + c.bp.rs_b[i]);
+            for (int i = 0; i < kLayers; ++i) add(DPRE[i], kG, dwp + c.bp.in_b[i]);
+            add(DH[0], kH, dwp + c.bp.start_b);
+            colsum_multi_kernel<ActT><<<dim3(R / 128, cj.count), 192, 0, side>>>(cj, R);
+            GLOW_CHECK_LAUNCH("colsum_multi_kernel");
+        }
         GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
         // ---- back on the main stream: 4x4 mix + ActNorm backward -> dz of the previous block
         const bool need_dz = k > 0 || dmel != nullptr;

@@ -43,6 +43,9 @@ int side_stream(SideStream **out)
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
         }
+        GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.enc_fork, cudaEventDisableTiming));
+        GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.enc_done, cudaEventDisableTiming));
+        s.enc_pending = false;
         g_side_init[dev] = true;
     }
     *out = &g_side[dev];

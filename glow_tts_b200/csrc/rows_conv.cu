@@ -71,6 +71,17 @@ rows_pack_kernel(const float *__restrict__ w, int cout, int cin, int taps, int b
     }
 }
 
+// grad[n][k][tap] += dwt[tap][k][n]   (cuBLAS result -> torch Conv1d layout, accumulated)
+__global__ void __launch_bounds__(256)
+rows_wgrad_accum_kernel(const float *__restrict__ dwt, float *__restrict__ grad, int cout, int cin, int taps)
+{
+    const int total = cout * cin * taps;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int n = i % cout, k = (i / cout) % cin, tap = i / (cout * cin);     // coalesced read of dwt
+        grad[((size_t)n * cin + k) * taps + tap] += dwt[i];
+    }
+}
+
 template <int N, int KP, int NP, int LD, int TAPS, int DIR>
 static int run_gemm(const float *a, const void *slab, const float *bias, float *out, const int32_t *row_utt, int rows_pad,
                     cudaStream_t st, const char *name, const glow_rows_conv_call *c = nullptr)
@@ -170,6 +181,48 @@ int glow_rows_conv_backward_weight(const glow_rows_conv_call *c, const float *x,
         GLOW_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, st));
         colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, st>>>(dy, c->cout, c->rows_pad, c->cout, dbias);
         GLOW_CHECK_LAUNCH("colsum_kernel");
+    }
+    return GLOW_OK;
+}
+
+int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *c, const float *x, const float *dy,
+                                         float *grad_w, float *grad_b, float *scratch)
+{
+    int shape;
+    int rc = check_rows(c, &shape);
+    if (rc) return rc;
+    GLOW_REQUIRE(x && dy && grad_w && scratch, GLOW_ERR_INVALID, "rows_conv_backward_weight_accum: null pointer");
+    SideStream *ss = nullptr;
+    rc = side_stream(&ss);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)c->stream, side = ss->stream;
+    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, st));
+    GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
+    const int center = (c->taps - 1) / 2;
+    rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout,
+                    scratch, c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
+    if (rc) return rc;
+    const int total = c->cin * c->cout * c->taps;
+    rows_wgrad_accum_kernel<<<(total + 255) / 256 < 2 * kNumSMs ? (total + 255) / 256 : 2 * kNumSMs, 256, 0, side>>>(
+        scratch, grad_w, c->cout, c->cin, c->taps);
+    GLOW_CHECK_LAUNCH("rows_wgrad_accum_kernel");
+    if (grad_b != nullptr) {
+        colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, side>>>(dy, c->cout, c->rows_pad, c->cout, grad_b);
+        GLOW_CHECK_LAUNCH("colsum_kernel");
+    }
+    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_done, side));
+    ss->enc_pending = true;
+    return GLOW_OK;
+}
+
+int glow_side_join(glow_stream_t stream)
+{
+    SideStream *ss = nullptr;
+    int rc = side_stream(&ss);
+    if (rc) return rc;
+    if (ss->enc_pending) {
+        GLOW_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->enc_done, 0));
+        ss->enc_pending = false;
     }
     return GLOW_OK;
 }

@@ -45,6 +45,15 @@ class TokenRows:
 
 
 _CACHE = {}
+ACCUMULATE = False       # set by train.TrainStep: weight gradients go straight into the attached .grad storage
+                         # on the side stream; whoever enables it must call join() before reading gradients
+PENDING = []             # tensors the side stream still reads; cleared by join()
+
+
+def join(device):
+    """Wait (stream-ordered) for the side-stream weight gradients; call before reading any .grad."""
+    _lib.side_join(device)
+    PENDING.clear()
 
 
 def token_rows(lengths, t_max, device):
@@ -93,6 +102,12 @@ class RowsConvFn(torch.autograd.Function):
                                                 _lib.ptr(bias.detach().contiguous()) if bias is not None else None,
                                                 _lib.ptr(y)), "glow_rows_conv_forward")
         ctx.tr, ctx.shape, ctx.has_bias, ctx.act = tr, (cin, cout, taps), bias is not None, (bool(relu), p, seed)
+        # accumulate-in-place mode: both gradients already live in (contiguous) flat storage
+        wg = weight.grad if (ACCUMULATE and weight.grad is not None and weight.grad.is_contiguous()) else None
+        bg = bias.grad if (wg is not None and bias is not None and bias.grad is not None) else None
+        if wg is not None and bias is not None and bg is None:
+            wg = None
+        ctx.grad_views = (wg, bg)
         ctx.save_for_backward(x, slab_wt, y if (relu or seed) else None)
         return y
 
@@ -119,7 +134,17 @@ class RowsConvFn(torch.autograd.Function):
                 dx = torch.empty((tr.rows_pad, cin), dtype=torch.float32, device=dev)
                 _lib.check(L.glow_rows_conv_backward_data(ctypes.byref(call), _lib.ptr(g), _lib.ptr(slab_wt),
                                                           _lib.ptr(dx)), "glow_rows_conv_backward_data")
-            if ctx.needs_input_grad[1]:
+            wg, bg = ctx.grad_views
+            if ctx.needs_input_grad[1] and wg is not None:
+                # straight into the parameters' gradient storage, on the side stream (joined by the caller
+                # through _lib.side_join before anything reads the gradients)
+                xm = x if ctx.x_masked else x * tr.valid
+                scratch = torch.empty((taps, cin, cout), dtype=torch.float32, device=dev)
+                _lib.check(L.glow_rows_conv_backward_weight_accum(ctypes.byref(call), _lib.ptr(xm), _lib.ptr(g),
+                                                                  _lib.ptr(wg), _lib.ptr(bg), _lib.ptr(scratch)),
+                           "glow_rows_conv_backward_weight_accum")
+                PENDING.append((xm, g, scratch))                  # alive until side_join
+            elif ctx.needs_input_grad[1]:
                 xm = x if ctx.x_masked else x * tr.valid          # the reduction runs over real rows only
                 dwt = torch.empty((taps, cin, cout), dtype=torch.float32, device=dev)
                 db = torch.empty(cout, dtype=torch.float32, device=dev) if ctx.has_bias else None

@@ -254,6 +254,14 @@ int glow_rows_conv_backward_data(const glow_rows_conv_call *call, const float *d
 int glow_rows_conv_backward_weight(const glow_rows_conv_call *call, const float *x, const float *dy,
                                    float *dw, float *dbias);
 
+/* Same reduction, ACCUMULATED into gradient buffers in torch's Conv1d layout (grad_w [cout, cin, taps] +=,
+ * grad_b [cout] +=, nullable) and run on the library's side stream so it overlaps the caller's stream:
+ * the call forks from `call->stream`; x, dy, scratch ([taps, cin, cout] floats) and the gradient buffers
+ * must stay untouched until glow_side_join(stream) has been enqueued, which makes `stream` wait for every
+ * accumulation forked so far. */
+int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *call, const float *x, const float *dy,
+                                         float *grad_w, float *grad_b, float *scratch);
+int glow_side_join(glow_stream_t stream);
 /* Gradient through the activation glow_rows_conv_forward fused on its output f [rows_pad, width]:
  * g = mask * dy * (relu ? [f != 0] : keep(row, col)) / (1 - p)   (f may be NULL when relu == 0). */
 int glow_rows_act_backward(const int32_t *row_utt, int rows_pad, int width, int relu, float p,

@@ -159,3 +159,26 @@ def test_rows_encoder_matches_torch_encoder(name):
         n = [k for k, q in enc.named_parameters() if q is p][0]
         tight = n.endswith(("Project.bias", "ANCRDCN_5.layer_Dict.Conv_1.weight"))
         assert rel_fro(a, b) < (2e-2 if tight else 1.5e-1), n
+
+
+def test_side_stream_weight_gradients_match_autograd_path():
+    """TrainStep lets the encoder convs accumulate their weight gradients into the flat gradient buffer
+    on the side stream; the result must equal the autograd path (gradients returned and accumulated by
+    torch) on the same step."""
+    from glow_tts_b200 import rows
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep
+    from tests._model_util import load_case
+    grads = []
+    for accumulate in (True, False):
+        model, sd, g, batch, mode = load_case("vanilla_small", "bf16")
+        model.eval()                                               # no dropout: the two runs are the same function
+        step = TrainStep(model, load_hparams(Mode=mode, Precision="bf16"), torch.device("cuda:0"))
+        step.opt.lr0, step.opt.wd, step.opt.max_norm = 0.0, 0.0, 0.0      # keep weights and gradients as they are
+        rows.ACCUMULATE = accumulate
+        step.run(step.to_device(batch))
+        torch.cuda.synchronize()
+        grads.append(step.flat.grad.detach().clone())
+    rows.ACCUMULATE = False
+    assert float(grads[0].abs().max()) > 0
+    assert rel_fro(grads[0], grads[1]) < 1e-5

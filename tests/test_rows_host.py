@@ -1,0 +1,63 @@
+"""Host-side logic of the packed-row encoder and of the captured train step (no GPU needed):
+row/gather index maps, the device-int cache, and the RAdam / Noam schedule `FusedRAdam.advance`
+hands to the kernels (against the oracle's restatement of Radam.py:57-76 / Noam_Scheduler.py:17-29)."""
+import math
+
+import numpy as np
+import torch
+
+
+def test_token_rows_pack_unpack_roundtrip_cpu():
+    from glow_tts_b200 import rows
+    lens, t_max = [7, 1, 12, 3], 12
+    tr = rows.TokenRows(lens, t_max, torch.device("cpu"))
+    assert tr.rows_pad % 128 == 0 and tr.rows_pad >= sum(lens) + 2 * (len(lens) + 1)
+    row_utt = tr.rm.row_utt.numpy()
+    assert (row_utt[:2] == -1).all() and (row_utt[-2:] == -1).all()           # leading / trailing guard rows
+    for b, n in enumerate(lens):
+        off = int(tr.rm.utt_off[b])
+        assert (row_utt[off:off + n] == b).all()
+        assert (row_utt[off - 2:off] == -1).all() and (row_utt[off + n:off + n + 2] == -1).all()
+    x = torch.randn(len(lens), t_max, 5)
+    packed = tr.pack(x)
+    assert packed.shape == (tr.rows_pad, 5)
+    assert float((packed * (1 - tr.valid)).abs().max()) == 0.0                # guard rows are zero
+    back = tr.unpack(packed)
+    mask = tr.tmask.unsqueeze(2)
+    assert torch.equal(back, x * mask)                                        # exact on real tokens, zero beyond
+    # a row holds the token (b, t) its map says
+    for r in np.flatnonzero(row_utt >= 0)[::5]:
+        b, t = int(row_utt[r]), int(tr.rm.row_t[r])
+        assert torch.equal(packed[r], x[b, t])
+
+
+def test_device_ints_are_cached():
+    from glow_tts_b200 import _lib
+    a = _lib.device_ints([3, 1, 2], torch.int32, "cpu")
+    b = _lib.device_ints((3, 1, 2), torch.int32, torch.device("cpu"))
+    assert a is b and a.dtype == torch.int32 and a.tolist() == [3, 1, 2]
+    assert _lib.device_ints([3, 1, 2], torch.int64, "cpu") is not a
+
+
+def test_fused_radam_schedule_matches_oracle():
+    from glow_tts_b200.flat import FlatBuffer
+    from glow_tts_b200.train import FusedRAdam
+    from oracle.glow_oracle import RAdamOracle
+    p = torch.nn.Parameter(torch.zeros(8))
+    opt = FusedRAdam(FlatBuffer([p]), lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-6, base=4000, max_norm=5.0)
+    ref = RAdamOracle([torch.zeros(8)])
+    for step in range(1, 12):
+        lr, b1, b2, eps, wd, step_size, rect, max_norm, grad_scale = opt.advance(grad_scale=0.5)
+        # the oracle's scalars for the same step
+        ref.t += 1
+        b2t = 0.999 ** ref.t
+        n_max = 2 / (1 - 0.999) - 1
+        n_sma = n_max - 2 * ref.t * b2t / (1 - b2t)
+        if n_sma >= 5:
+            want = math.sqrt((1 - b2t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) / (1 - 0.9 ** ref.t)
+        else:
+            want = 1.0 / (1 - 0.9 ** ref.t)
+        assert lr == ref.lr() and step_size == want and rect == float(n_sma >= 5)
+        assert (b1, b2, eps, wd, max_norm, grad_scale) == (0.9, 0.999, 1e-6, 1e-6, 5.0, 0.5)
+        ref.epoch += 1
+    assert opt.steps == 11 and opt.epoch == 11

@@ -15,6 +15,7 @@
 // Backward is two kernels: per query tile (dP, dS, dQ, dwK, dwV) and per key
 // tile (dK, dV); dS goes through a [B,H,T,T] scratch.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace glow {
 
@@ -385,6 +386,412 @@ rpr_attn_bwd_kv_kernel(const AttnArgs a)
     store_tile_T(Qs, a.dk, a, b, h, j0, tid);
 }
 
+// =====================================================================================
+// Tensor-core forward for the packed-row layout (the encoder path): Q.K^T and Pd.V on
+// mma.sync m16n8k16 (bf16 operands, fp32 accumulate), softmax / masks / dropout / band terms
+// in fp32.  One CTA = 64 queries of one (sentence, head); K, V of the whole sentence (<= 208
+// tokens) sit in shared memory as bf16, the 64 x T score tile as fp32.  Warp w owns query rows
+// 16w .. 16w+15 from the first MMA to the store, so the phases only need __syncwarp.
+// =====================================================================================
+constexpr int kMQ = 64;                 // queries per CTA
+constexpr int kMT = 208;                // longest sentence the tile holds (T_text <= 200 + <S>/<E>)
+constexpr int kMP = kAD + 8;            // bf16 row pitch: 208 B -> conflict-free ldmatrix rows
+constexpr int kMSP = kMT + 4;           // fp32 score row pitch
+constexpr int kMThreads = 128;
+constexpr size_t kMSmem = (size_t)(kMQ + 2 * kMT + 16) * kMP * 2 + (size_t)kAMaxRel * kAD * 4 +
+                          (size_t)kMQ * kMSP * 4 + (size_t)kMQ * 16 * 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void *p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_addr(p)));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void *p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(smem_addr(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi)
+{
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+// rows [t0, t0 + n) of one head of a packed-row tensor -> bf16 tile rows (zeros beyond the sentence)
+__device__ __forceinline__ void load_rows_bf16(__nv_bfloat16 *tile, const float *base, int ld, int t0, int n, int len, int tid)
+{
+    for (int e = tid; e < n * (kAD / 4); e += kMThreads) {
+        const int r = e / (kAD / 4), c4 = e - r * (kAD / 4);
+        const int t = t0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < len) v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)t * ld) + c4);
+        *reinterpret_cast<uint2 *>(tile + (size_t)r * kMP + c4 * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    }
+}
+
+__global__ void __launch_bounds__(kMThreads)
+rpr_attn_fwd_mma_kernel(const AttnArgs a)
+{
+    const uint64_t seed = attn_seed(a);
+    extern __shared__ __align__(16) unsigned char raw[];
+    __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(raw);
+    __nv_bfloat16 *Ks = Qs + kMQ * kMP;
+    __nv_bfloat16 *Vs = Ks + kMT * kMP;
+    __nv_bfloat16 *Rk = Vs + kMT * kMP;
+    float *Wv = reinterpret_cast<float *>(Rk + 16 * kMP);
+    float *S = Wv + kAMaxRel * kAD;
+    float *AR = S + kMQ * kMSP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * kMQ, h = blockIdx.y, b = blockIdx.z;
+    const int len = a.lengths[b], T = a.T, nrel = 2 * a.window + 1, w = a.window;
+    if (i0 >= len) return;
+    const int TK = min(kMT, (len + 15) & ~15);
+    const size_t off = (size_t)a.utt_off[b] * a.ld + h * kAD;
+    load_rows_bf16(Qs, a.q + off, a.ld, i0, kMQ, len, tid);
+    load_rows_bf16(Ks, a.k + off, a.ld, 0, TK, len, tid);
+    load_rows_bf16(Vs, a.v + off, a.ld, 0, TK, len, tid);
+    for (int e = tid; e < 16 * kAD; e += kMThreads) {
+        const int r = e / kAD, d = e - r * kAD;
+        Rk[r * kMP + d] = __float2bfloat16(r < nrel ? a.wk[r * kAD + d] : 0.f);
+    }
+    for (int e = tid; e < nrel * kAD; e += kMThreads) Wv[e] = a.wv[e];
+    __syncthreads();
+
+    const int m0 = warp * 16, g = lane >> 2, t2 = (lane & 3) * 2;
+    // ---- S = Q K^T, AR = Q wK^T
+    {
+        uint32_t af[kAD / 16][4];
+#pragma unroll
+        for (int kk = 0; kk < kAD / 16; ++kk) ldsm_x4(af[kk], Qs + (m0 + (lane & 15)) * kMP + kk * 16 + (lane >> 4) * 8);
+        for (int nt = 0; nt < TK / 8 + 2; ++nt) {
+            const bool rel = nt >= TK / 8;
+            const __nv_bfloat16 *Bt = rel ? Rk + (nt - TK / 8) * 8 * kMP : Ks + nt * 8 * kMP;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kk = 0; kk < kAD / 16; ++kk) {
+                uint32_t bf[2];
+                ldsm_x2(bf, Bt + (lane & 7) * kMP + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma_bf16(c, af[kk], bf);
+            }
+            float *dst = rel ? AR + (nt - TK / 8) * 8 : S + nt * 8;
+            const int pitch = rel ? 16 : kMSP;
+            *reinterpret_cast<float2 *>(dst + (m0 + g) * pitch + t2) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2 *>(dst + (m0 + g + 8) * pitch + t2) = make_float2(c[2], c[3]);
+        }
+    }
+    __syncwarp();
+    // ---- softmax (+ dropout) of this warp's 16 rows (RPR_MHA.py:109-120)
+    const float inv_keep = 1.f / (1.f - a.drop_p);
+    for (int rr = 0; rr < 16; ++rr) {
+        const int i = m0 + rr, gi = i0 + i;
+        float *row = S + i * kMSP;
+        if (gi >= len) {                                         // a padding query: contributes nothing
+            for (int j = lane; j < TK; j += 32) row[j] = 0.f;
+            continue;
+        }
+        float mx = -INFINITY;
+        for (int j = lane; j < len; j += 32) {
+            const int r = j - gi + w;
+            const float sc = (row[j] + ((r >= 0 && r < nrel) ? AR[i * 16 + r] : 0.f)) * a.scale;
+            row[j] = sc;
+            mx = fmaxf(mx, sc);
+        }
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < len; j += 32) { const float e = __expf(row[j] - mx); row[j] = e; sum += e; }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        const size_t base = ((size_t)(b * a.H + h) * T + gi) * T;
+        for (int j = lane; j < len; j += 32) {
+            const float p = row[j] * inv;
+            if (a.probs != nullptr) a.probs[base + j] = p;
+            float pd = p;
+            if (seed != 0) pd = attn_keep(seed, base + j, a.drop_p) ? p * inv_keep : 0.f;
+            if (a.align != nullptr) a.align[base + j] = pd;
+            row[j] = pd;
+        }
+        for (int j = len + lane; j < T; j += 32) {               // masked keys: exp(-1e4 - max) == 0 in fp32
+            if (a.probs != nullptr) a.probs[base + j] = 0.f;
+            if (a.align != nullptr) a.align[base + j] = 0.f;
+        }
+        for (int j = len + lane; j < TK; j += 32) row[j] = 0.f;
+    }
+    __syncwarp();
+    // ---- O = Pd V + band(Pd, wV)
+    float o[kAD / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kAD / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+    const float *r0 = S + (m0 + g) * kMSP, *r1 = S + (m0 + g + 8) * kMSP;
+    for (int kt = 0; kt < TK / 16; ++kt) {
+        const int k0 = kt * 16 + t2;
+        uint32_t pa[4];
+        pa[0] = pack2(r0[k0], r0[k0 + 1]);
+        pa[1] = pack2(r1[k0], r1[k0 + 1]);
+        pa[2] = pack2(r0[k0 + 8], r0[k0 + 9]);
+        pa[3] = pack2(r1[k0 + 8], r1[k0 + 9]);
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt) {
+            uint32_t vb[2];
+            ldsm_x2_trans(vb, Vs + (kt * 16 + (lane & 15)) * kMP + nt * 8);
+            mma_bf16(o[nt], pa, vb);
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int i = m0 + g + 8 * hh, gi = i0 + i;
+        if (gi >= len) continue;
+        const float *row = S + i * kMSP;
+        for (int r = 0; r < nrel; ++r) {
+            const int j = gi + r - w;
+            if (j < 0 || j >= len) continue;
+            const float p = row[j];
+#pragma unroll
+            for (int nt = 0; nt < kAD / 8; ++nt) {
+                const float2 wv = *reinterpret_cast<const float2 *>(Wv + r * kAD + nt * 8 + t2);
+                o[nt][2 * hh] = fmaf(p, wv.x, o[nt][2 * hh]);
+                o[nt][2 * hh + 1] = fmaf(p, wv.y, o[nt][2 * hh + 1]);
+            }
+        }
+        float *dst = a.out + off + (size_t)gi * a.ld;
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt)
+            *reinterpret_cast<float2 *>(dst + nt * 8 + t2) = make_float2(o[nt][2 * hh], o[nt][2 * hh + 1]);
+    }
+}
+
+// ---- tensor-core backward, query tiles: dPd = dO V^T (+ band), softmax backward, dS scratch,
+//      dQ = dS K (+ band), dwK, dwV.  Same tile shape and ownership as the forward kernel.
+constexpr size_t kMSmemBq = kMSmem + (size_t)kMQ * 16 * 4;
+
+__global__ void __launch_bounds__(kMThreads)
+rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
+{
+    const uint64_t seed = attn_seed(a);
+    extern __shared__ __align__(16) unsigned char raw[];
+    __nv_bfloat16 *Ds = reinterpret_cast<__nv_bfloat16 *>(raw);          // dO tile
+    __nv_bfloat16 *Ks = Ds + kMQ * kMP;
+    __nv_bfloat16 *Vs = Ks + kMT * kMP;
+    __nv_bfloat16 *Rv = Vs + kMT * kMP;                                  // wV as 16 bf16 "key" rows
+    float *Wk = reinterpret_cast<float *>(Rv + 16 * kMP);
+    float *S = Wk + kAMaxRel * kAD;
+    float *AR = S + kMQ * kMSP;                                          // dO.wV[r], then Pd on the band
+    float *BS = AR + kMQ * 16;                                           // dS on the band
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * kMQ, h = blockIdx.y, b = blockIdx.z;
+    const int len = a.lengths[b], T = a.T, nrel = 2 * a.window + 1, w = a.window;
+    if (i0 >= len) return;
+    const int TK = min(kMT, (len + 15) & ~15);
+    const size_t off = (size_t)a.utt_off[b] * a.ld + h * kAD;
+    load_rows_bf16(Ds, a.dout + off, a.ld, i0, kMQ, len, tid);
+    load_rows_bf16(Ks, a.k + off, a.ld, 0, TK, len, tid);
+    load_rows_bf16(Vs, a.v + off, a.ld, 0, TK, len, tid);
+    for (int e = tid; e < 16 * kAD; e += kMThreads) {
+        const int r = e / kAD, d = e - r * kAD;
+        Rv[r * kMP + d] = __float2bfloat16(r < nrel ? a.wv[r * kAD + d] : 0.f);
+    }
+    for (int e = tid; e < nrel * kAD; e += kMThreads) Wk[e] = a.wk[e];
+    __syncthreads();
+
+    const int m0 = warp * 16, g = lane >> 2, t2 = (lane & 3) * 2;
+    {   // dPd = dO V^T ; AR = dO wV^T
+        uint32_t af[kAD / 16][4];
+#pragma unroll
+        for (int kk = 0; kk < kAD / 16; ++kk) ldsm_x4(af[kk], Ds + (m0 + (lane & 15)) * kMP + kk * 16 + (lane >> 4) * 8);
+        for (int nt = 0; nt < TK / 8 + 2; ++nt) {
+            const bool rel = nt >= TK / 8;
+            const __nv_bfloat16 *Bt = rel ? Rv + (nt - TK / 8) * 8 * kMP : Vs + nt * 8 * kMP;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kk = 0; kk < kAD / 16; ++kk) {
+                uint32_t bf[2];
+                ldsm_x2(bf, Bt + (lane & 7) * kMP + kk * 16 + ((lane >> 3) & 1) * 8);
+                mma_bf16(c, af[kk], bf);
+            }
+            float *dst = rel ? AR + (nt - TK / 8) * 8 : S + nt * 8;
+            const int pitch = rel ? 16 : kMSP;
+            *reinterpret_cast<float2 *>(dst + (m0 + g) * pitch + t2) = make_float2(c[0], c[1]);
+            *reinterpret_cast<float2 *>(dst + (m0 + g + 8) * pitch + t2) = make_float2(c[2], c[3]);
+        }
+    }
+    __syncwarp();
+    // rows: dP = dPd * keep/(1-p); dS = P (dP - sum_j dP P) * scale  (RPR_MHA.py:117-120 backward)
+    const float inv_keep = 1.f / (1.f - a.drop_p);
+    for (int rr = 0; rr < 16; ++rr) {
+        const int i = m0 + rr, gi = i0 + i;
+        float *row = S + i * kMSP;
+        if (gi >= len) {
+            for (int j = lane; j < TK; j += 32) row[j] = 0.f;
+            if (lane < 16) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
+            continue;
+        }
+        const size_t base = ((size_t)(b * a.H + h) * T + gi) * T;
+        float dot = 0.f;
+        for (int j = lane; j < len; j += 32) {
+            const int r = j - gi + w;
+            float dp = row[j] + ((r >= 0 && r < nrel) ? AR[i * 16 + r] : 0.f);
+            if (seed != 0) dp = attn_keep(seed, base + j, a.drop_p) ? dp * inv_keep : 0.f;
+            row[j] = dp;
+            dot = fmaf(dp, a.probs[base + j], dot);
+        }
+        for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        __syncwarp();                                            // AR[i][*] has been consumed
+        for (int j = lane; j < len; j += 32) {
+            const float p = a.probs[base + j];
+            const float ds = p * (row[j] - dot) * a.scale;
+            row[j] = ds;
+            a.ds[base + j] = ds;
+            const int r = j - gi + w;
+            if (r >= 0 && r < nrel) {                            // keep the band of Pd and dS for dwV / dwK
+                float pd = p;
+                if (seed != 0) pd = attn_keep(seed, base + j, a.drop_p) ? p * inv_keep : 0.f;
+                AR[i * 16 + r] = pd;
+                BS[i * 16 + r] = ds;
+            }
+        }
+        if (lane < nrel) {                                       // band positions outside the sentence
+            const int j = gi + lane - w;
+            if (j < 0 || j >= len) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
+        }
+        for (int j = len + lane; j < TK; j += 32) row[j] = 0.f;
+    }
+    __syncwarp();
+    // dQ = dS K + band(dS, wK)
+    float o[kAD / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kAD / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+    const float *r0 = S + (m0 + g) * kMSP, *r1 = S + (m0 + g + 8) * kMSP;
+    for (int kt = 0; kt < TK / 16; ++kt) {
+        const int k0 = kt * 16 + t2;
+        uint32_t pa[4];
+        pa[0] = pack2(r0[k0], r0[k0 + 1]);
+        pa[1] = pack2(r1[k0], r1[k0 + 1]);
+        pa[2] = pack2(r0[k0 + 8], r0[k0 + 9]);
+        pa[3] = pack2(r1[k0 + 8], r1[k0 + 9]);
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt) {
+            uint32_t kb[2];
+            ldsm_x2_trans(kb, Ks + (kt * 16 + (lane & 15)) * kMP + nt * 8);
+            mma_bf16(o[nt], pa, kb);
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int i = m0 + g + 8 * hh, gi = i0 + i;
+        if (gi >= len) continue;
+        for (int r = 0; r < nrel; ++r) {
+            const float dsv = BS[i * 16 + r];
+#pragma unroll
+            for (int nt = 0; nt < kAD / 8; ++nt) {
+                const float2 wk = *reinterpret_cast<const float2 *>(Wk + r * kAD + nt * 8 + t2);
+                o[nt][2 * hh] = fmaf(dsv, wk.x, o[nt][2 * hh]);
+                o[nt][2 * hh + 1] = fmaf(dsv, wk.y, o[nt][2 * hh + 1]);
+            }
+        }
+        float *dst = a.dq + off + (size_t)gi * a.ld;
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt)
+            *reinterpret_cast<float2 *>(dst + nt * 8 + t2) = make_float2(o[nt][2 * hh], o[nt][2 * hh + 1]);
+    }
+    __syncthreads();
+    // dwV[r][e] += sum_i Pd[i][i+r-w] dO[i][e] ; dwK[r][e] += sum_i dS[i][i+r-w] q[i][e]   (this tile's 64 queries)
+    for (int e = tid; e < nrel * kAD; e += kMThreads) {
+        const int r = e / kAD, d = e - r * kAD;
+        float accv = 0.f, acck = 0.f;
+        for (int i = 0; i < kMQ; ++i) {
+            const int gi = i0 + i;
+            if (gi >= len) break;
+            accv = fmaf(AR[i * 16 + r], __bfloat162float(Ds[i * kMP + d]), accv);
+            acck = fmaf(BS[i * 16 + r], __ldg(a.q + off + (size_t)gi * a.ld + d), acck);
+        }
+        atomicAdd(a.dwv + e, accv);
+        atomicAdd(a.dwk + e, acck);
+    }
+}
+
+// ---- tensor-core backward, key tiles: dV[j] = sum_i Pd[i][j] dO[i] ; dK[j] = sum_i dS[i][j] q[i]
+constexpr int kMKP = kMQ + 4;            // fp32 pitch of the [query][64 keys] tiles
+constexpr size_t kMSmemKv = (size_t)2 * kMT * kMP * 2 + (size_t)2 * kMT * kMKP * 4;
+
+__global__ void __launch_bounds__(kMThreads)
+rpr_attn_bwd_kv_mma_kernel(const AttnArgs a)
+{
+    const uint64_t seed = attn_seed(a);
+    extern __shared__ __align__(16) unsigned char raw[];
+    __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(raw);
+    __nv_bfloat16 *Ds = Qs + kMT * kMP;
+    float *Pt = reinterpret_cast<float *>(Ds + kMT * kMP);               // Pd[i][j0 + jj]
+    float *St = Pt + kMT * kMKP;                                         // dS[i][j0 + jj]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * kMQ, h = blockIdx.y, b = blockIdx.z;
+    const int len = a.lengths[b], T = a.T;
+    if (j0 >= len) return;
+    const int TQ = min(kMT, (len + 15) & ~15);
+    const size_t off = (size_t)a.utt_off[b] * a.ld + h * kAD;
+    const float inv_keep = 1.f / (1.f - a.drop_p);
+    load_rows_bf16(Qs, a.q + off, a.ld, 0, TQ, len, tid);
+    load_rows_bf16(Ds, a.dout + off, a.ld, 0, TQ, len, tid);
+    for (int e = tid; e < TQ * kMQ; e += kMThreads) {
+        const int i = e >> 6, jj = e & 63;
+        const int j = j0 + jj;
+        float pd = 0.f, ds = 0.f;
+        if (i < len && j < len) {
+            const size_t idx = ((size_t)(b * a.H + h) * T + i) * T + j;
+            pd = a.probs[idx];
+            if (seed != 0) pd = attn_keep(seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
+            ds = a.ds[idx];
+        }
+        Pt[i * kMKP + jj] = pd;
+        St[i * kMKP + jj] = ds;
+    }
+    __syncthreads();
+    const int m0 = warp * 16, g = lane >> 2, t2 = (lane & 3) * 2;
+    float dv[kAD / 8][4], dk[kAD / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kAD / 8; ++nt) {
+        dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+        dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+    }
+    for (int kt = 0; kt < TQ / 16; ++kt) {
+        // A = (tile)^T: element (key m, query k) = tile[k][m]
+        const float *p0 = Pt + (kt * 16 + t2) * kMKP + m0 + g, *s0 = St + (kt * 16 + t2) * kMKP + m0 + g;
+        uint32_t pa[4], sa[4];
+        pa[0] = pack2(p0[0], p0[kMKP]);               pa[1] = pack2(p0[8], p0[kMKP + 8]);
+        pa[2] = pack2(p0[8 * kMKP], p0[9 * kMKP]);    pa[3] = pack2(p0[8 * kMKP + 8], p0[9 * kMKP + 8]);
+        sa[0] = pack2(s0[0], s0[kMKP]);               sa[1] = pack2(s0[8], s0[kMKP + 8]);
+        sa[2] = pack2(s0[8 * kMKP], s0[9 * kMKP]);    sa[3] = pack2(s0[8 * kMKP + 8], s0[9 * kMKP + 8]);
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt) {
+            uint32_t bd[2], bq[2];
+            ldsm_x2_trans(bd, Ds + (kt * 16 + (lane & 15)) * kMP + nt * 8);
+            ldsm_x2_trans(bq, Qs + (kt * 16 + (lane & 15)) * kMP + nt * 8);
+            mma_bf16(dv[nt], pa, bd);
+            mma_bf16(dk[nt], sa, bq);
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int j = j0 + m0 + g + 8 * hh;
+        if (j >= len) continue;
+        float *dvp = a.dv + off + (size_t)j * a.ld, *dkp = a.dk + off + (size_t)j * a.ld;
+#pragma unroll
+        for (int nt = 0; nt < kAD / 8; ++nt) {
+            *reinterpret_cast<float2 *>(dvp + nt * 8 + t2) = make_float2(dv[nt][2 * hh], dv[nt][2 * hh + 1]);
+            *reinterpret_cast<float2 *>(dkp + nt * 8 + t2) = make_float2(dk[nt][2 * hh], dk[nt][2 * hh + 1]);
+        }
+    }
+}
+
 static int check_attn(const glow_attn_call *c)
 {
     GLOW_REQUIRE(c != nullptr, GLOW_ERR_INVALID, "attention: null call");
@@ -428,6 +835,16 @@ int glow_rpr_attention_forward(const glow_attn_call *c, float *out, float *probs
     GLOW_REQUIRE(out != nullptr, GLOW_ERR_INVALID, "attention_forward: null out");
     AttnArgs a = to_args(c);
     a.out = out; a.probs = probs; a.align = align;
+    if (a.utt_off != nullptr && c->t <= kMT && 2 * c->window + 1 <= 16 && getenv("GLOW_ATTN_SIMT") == nullptr) {
+        // packed rows, sentence fits the shared-memory tile: tensor-core path
+        GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kMSmem));
+        dim3 grid((c->t + kMQ - 1) / kMQ, c->heads, c->batch);
+        ProfScope prof("rpr_attn_fwd", (cudaStream_t)c->stream);
+        rpr_attn_fwd_mma_kernel<<<grid, kMThreads, kMSmem, (cudaStream_t)c->stream>>>(a);
+        GLOW_CHECK_LAUNCH("rpr_attn_fwd_mma_kernel");
+        return GLOW_OK;
+    }
     const size_t smem = attn_smem_bytes(c->t);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c->t + kAQ - 1) / kAQ, c->heads, c->batch);
@@ -451,6 +868,19 @@ int glow_rpr_attention_backward(const glow_attn_call *c, const float *dout, cons
     const size_t nrel = (size_t)(2 * c->window + 1) * c->head_dim;
     GLOW_CHECK_CUDA(cudaMemsetAsync(dwk, 0, sizeof(float) * nrel, st));
     GLOW_CHECK_CUDA(cudaMemsetAsync(dwv, 0, sizeof(float) * nrel, st));
+    if (a.utt_off != nullptr && c->t <= kMT && 2 * c->window + 1 <= 16 && getenv("GLOW_ATTN_SIMT") == nullptr) {
+        GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_bwd_q_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kMSmemBq));
+        GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_bwd_kv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kMSmemKv));
+        dim3 grid((c->t + kMQ - 1) / kMQ, c->heads, c->batch);
+        ProfScope prof("rpr_attn_bwd", st);
+        rpr_attn_bwd_q_mma_kernel<<<grid, kMThreads, kMSmemBq, st>>>(a);
+        GLOW_CHECK_LAUNCH("rpr_attn_bwd_q_mma_kernel");
+        rpr_attn_bwd_kv_mma_kernel<<<grid, kMThreads, kMSmemKv, st>>>(a);
+        GLOW_CHECK_LAUNCH("rpr_attn_bwd_kv_mma_kernel");
+        return GLOW_OK;
+    }
     const size_t smem = attn_smem_bytes(c->t);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(rpr_attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c->t + kAQ - 1) / kAQ, c->heads, c->batch);

@@ -48,3 +48,40 @@ def test_attention_dropout_is_statistical_and_consistent():
     assert abs(kept - 0.9) < 0.02
     nz = a_train[0, :, :n, :n] != 0
     assert rel_err(a_train[0, :, :n, :n][nz], (a_eval[0, :, :n, :n] / 0.9)[nz]) < 1e-5
+
+
+def test_rows_tensor_core_forward_matches_cuda_core_kernel():
+    """Packed-row layout: Q.K^T and Pd.V on mma.sync (bf16 operands) against the fp32 CUDA-core kernels
+    on the [B,C,T] layout, same inputs, eval mode.  bf16 operand rounding: 2e-2 of the largest output."""
+    import torch
+    from glow_tts_b200 import rows
+    from glow_tts_b200.rpr_mha import _AttnCoreFn, _AttnRowsFn
+    torch.manual_seed(11)
+    dev = torch.device("cuda:0")
+    lens, t_max, heads, d, window = [150, 64, 7, 201, 33], 201, 2, 96, 4
+    tr = rows.token_rows(lens, t_max, dev)
+    lengths = torch.tensor(lens, dtype=torch.int32, device=dev)
+    q, k, v = (torch.randn(len(lens), heads * d, t_max, device=dev) * tr.tmask.unsqueeze(1) for _ in range(3))
+    wk = torch.randn(1, 2 * window + 1, d, device=dev) * d ** -0.5
+    wv = torch.randn(1, 2 * window + 1, d, device=dev) * d ** -0.5
+    for x in (q, k, v, wk, wv):
+        x.requires_grad_(True)
+    want, _ = _AttnCoreFn.apply(q, k, v, wk, wv, lengths, None, heads, window, 0.0, 0, False)
+    qr, kr, vr = (tr.pack(x.detach().transpose(1, 2).contiguous()).requires_grad_(True) for x in (q, k, v))
+    wk2, wv2 = wk.detach().clone().requires_grad_(True), wv.detach().clone().requires_grad_(True)
+    got_rows = _AttnRowsFn.apply(qr, kr, vr, wk2, wv2, tr, lengths, heads, window, 0.0, 0)
+    got = tr.unpack(got_rows).transpose(1, 2)
+    want = want * tr.tmask.unsqueeze(1)                            # the [B,C,T] kernel also fills padded queries
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-2, err
+    assert float((got_rows * (1 - tr.valid)).abs().max()) == 0.0   # guard rows untouched (zeros)
+    # backward: same upstream gradient through both implementations
+    gsrc = torch.randn(len(lens), heads * d, t_max, device=dev) * tr.tmask.unsqueeze(1)
+    (want * gsrc).sum().backward()
+    got_rows.backward(tr.pack(gsrc.transpose(1, 2).contiguous()))
+    def unp(x):
+        return tr.unpack(x).transpose(1, 2)
+    for name, a, b in (("dq", unp(qr.grad), q.grad * tr.tmask.unsqueeze(1)), ("dk", unp(kr.grad), k.grad * tr.tmask.unsqueeze(1)),
+                       ("dv", unp(vr.grad), v.grad * tr.tmask.unsqueeze(1)), ("dwk", wk2.grad, wk.grad), ("dwv", wv2.grad, wv.grad)):
+        e = float((a - b).abs().max() / b.abs().max())
+        assert e < 3e-2, (name, e)

@@ -400,12 +400,10 @@ struct EpiBwdGate {
             dins[2 * j] = m ? v[j] * s * (1.f - t * t) : 0.f;
             dins[2 * j + 1] = m ? v[j] * t * s * (1.f - s) : 0.f;
         }
-        st_vec<2 * NV>(DINS + (size_t)row * kG + 2 * n0, dins);
-        if (DPRE != DINS) {
+        if (DINS != nullptr) st_vec<2 * NV>(DINS + (size_t)row * kG + 2 * n0, dins);     // only the speaker bias reads it
 #pragma unroll
-            for (int j = 0; j < NV; ++j) drop.apply2(dins[2 * j], dins[2 * j + 1], row, 2 * (n0 + j));
-            st_vec<2 * NV>(DPRE + (size_t)row * kG + 2 * n0, dins);
-        }
+        for (int j = 0; j < NV; ++j) drop.apply2(dins[2 * j], dins[2 * j + 1], row, 2 * (n0 + j));
+        st_vec<2 * NV>(DPRE + (size_t)row * kG + 2 * n0, dins);
     }
 };
 

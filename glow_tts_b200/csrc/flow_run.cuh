@@ -244,7 +244,7 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
             const ActT *DHnext = last ? nullptr : DH[i + 1];
-            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, DINS, DPRE[i]));
+            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, c.spk != nullptr ? DINS : nullptr, DPRE[i]));
             if (c.spk != nullptr) {
                 float *dspkb = c.bw_f32 + c.wl.dspkb;
                 seg_colsum_kernel<ActT><<<dim3(kG / 128, B), 128, 0, c.st>>>(DINS, kG, kG, c.rows.utt_off,

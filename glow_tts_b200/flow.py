@@ -56,6 +56,30 @@ def row_map(sq_lengths, device):
     return rm
 
 
+# ---- side stream for work that is off the step's critical path ------------------------------
+# The per-step weight preparation (weight_norm -> packed / slab images) only depends on the parameters,
+# so it can run while the text encoder does; the way back from effective-weight gradients to parameter
+# gradients only feeds the optimizer, so it can run while the encoder's backward does.  Both go to one
+# torch side stream per device; join() makes the current stream wait for it.  (Stream fork / join is
+# capturable, so the overlap survives in the CUDA graph.)
+_SIDE = {}
+_SIDE_BUSY = set()
+
+
+def side_stream(device):
+    key = str(torch.device(device))
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
+
+
+def join(device):
+    key = str(torch.device(device))
+    if key in _SIDE_BUSY:
+        torch.cuda.current_stream(device).wait_stream(_SIDE[key])
+        _SIDE_BUSY.discard(key)
+
+
 def precision_tag(precision):
     if precision in ("fp32", "f32", torch.float32):
         return _lib.GLOW_F32, torch.float32
@@ -152,7 +176,12 @@ class FlowDecoderFn(torch.autograd.Function):
         spk_c = spk.contiguous().float() if spk is not None else None
         b, _, t = mel.shape
         with torch.cuda.device(device):
-            wp, wtc = plan.prepare(flat, offs, device, tag)
+            if owner._prepared is not None:                       # started early on the side stream (begin_prepare)
+                wp, wtc = owner._prepared
+                owner._prepared = None
+                join(device)
+            else:
+                wp, wtc = plan.prepare(flat, offs, device, tag)
             ws = plan.workspace(rm, device, act_dtype, training)
             call = plan.call_struct(rm, t, tag, wp, wtc, spk_c, ws, training, seed, device)
             z = torch.empty_like(mel)
@@ -189,10 +218,23 @@ class FlowDecoderFn(torch.autograd.Function):
             rc = _lib.lib().glow_flow_backward(ctypes.byref(call), _lib.ptr(dz), _lib.ptr(dlogdet), _lib.ptr(dwp),
                                                _lib.ptr(dmel), _lib.ptr(dspk))
             _lib.check(rc, "glow_flow_backward")
-            rc = _lib.lib().glow_flow_param_grads(ctypes.byref(plan.cfg), _lib.ptr(flat), offs.ctypes.data,
-                                                  _lib.ptr(wp), _lib.ptr(dwp), _lib.ptr(dlogdet),
-                                                  rm.utt_len.data_ptr(), rm.batch, _lib.ptr(gflat),
-                                                  _lib.stream_ptr(device))
+            if direct and owner.defer_param_grads:
+                # gradients land in the attached flat buffer: nothing downstream in autograd needs them, so
+                # the conversion runs on the side stream (the owner of the step joins before the optimizer)
+                cur, side = torch.cuda.current_stream(device), side_stream(device)
+                side.wait_stream(cur)
+                dlogdet.record_stream(side)
+                with torch.cuda.stream(side):
+                    rc = _lib.lib().glow_flow_param_grads(ctypes.byref(plan.cfg), _lib.ptr(flat), offs.ctypes.data,
+                                                          _lib.ptr(wp), _lib.ptr(dwp), _lib.ptr(dlogdet),
+                                                          rm.utt_len.data_ptr(), rm.batch, _lib.ptr(gflat),
+                                                          _lib.stream_ptr(device))
+                _SIDE_BUSY.add(str(torch.device(device)))
+            else:
+                rc = _lib.lib().glow_flow_param_grads(ctypes.byref(plan.cfg), _lib.ptr(flat), offs.ctypes.data,
+                                                      _lib.ptr(wp), _lib.ptr(dwp), _lib.ptr(dlogdet),
+                                                      rm.utt_len.data_ptr(), rm.batch, _lib.ptr(gflat),
+                                                      _lib.stream_ptr(device))
             _lib.check(rc, "glow_flow_param_grads")
         if direct:        # gradients were accumulated straight into the .grad views
             pgrads = (None,) * ctx.n_params

@@ -213,6 +213,8 @@ class Decoder(torch.nn.Module):
         self._offs = None
         self._step = 0
         self.host_lengths = None       # optional: set by the caller to skip the D2H sync
+        self._prepared = None          # (wpack, wpack_tc) being prepared on the side stream (begin_prepare)
+        self.defer_param_grads = False  # set by train.TrainStep, which joins the side stream before the optimizer
 
     # ---- flat parameter plumbing (see flat.py) ------------------------------------
     def slot_params(self):
@@ -251,6 +253,19 @@ class Decoder(torch.nn.Module):
         if blocks not in self._plans:
             self._plans[blocks] = _flow.FlowPlan(blocks, self.spk_dim, self.dropout)
         return self._plans[blocks]
+
+    def begin_prepare(self, device):
+        """Start this step's weight preparation on the side stream (it only depends on the parameters);
+        the next forward() picks the result up.  Skipped while ActNorm still needs its data-dependent init."""
+        if self._prepared is not None or not all(blk.layers[0].initialized for blk in self.layer_Dict["Flows"]):
+            return
+        tag, _ = _flow.precision_tag(self.precision)
+        flat, offs = self.flat_params()
+        cur, side = torch.cuda.current_stream(device), _flow.side_stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.device(device), torch.cuda.stream(side):
+            self._prepared = self.plan.prepare(flat, offs, device, tag)
+        _flow._SIDE_BUSY.add(str(torch.device(device)))
 
     # ---- ActNorm data-dependent init (Modules.py:685-711) -----------------------------
     @torch.no_grad()
@@ -617,9 +632,11 @@ class GlowTTS(torch.nn.Module):
         t_len = _lib.device_ints(tl, torch.int32, dev)
         m_len = _lib.device_ints(ml, torch.int32, dev)
 
+        dec = d["Decoder"]
+        if torch.is_grad_enabled():
+            dec.begin_prepare(dev)                 # weight_norm / slab images while the encoder runs
         mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk, None,
                                                            lengths=t_len, host_lengths=tl)
-        dec = d["Decoder"]
         dec.host_lengths = ml
         try:
             z, log_dets, mel_masks = dec(mels[:, :, :max(ml)], mel_masks, spk, None, None)

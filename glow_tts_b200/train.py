@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import _lib, modules, rows as _rows
+from . import _lib, flow as _flow, modules, rows as _rows
 
 
 class FusedRAdam:
@@ -122,7 +122,8 @@ class TrainStep:
         # device step counter: mixed into the kernels' dropout seeds (see _lib.set_step_counter)
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
         _lib.set_step_counter(device, self.step_counter)
-        _rows.ACCUMULATE = True          # run() joins the side stream before it touches the gradients
+        _rows.ACCUMULATE = True          # run() joins the side streams before it touches the gradients
+        model.layer_Dict["Decoder"].defer_param_grads = True
 
     def to_device(self, batch_host):
         """H2D of one collated batch (pinned -> device, async).  Lengths stay on the host too."""
@@ -158,6 +159,7 @@ class TrainStep:
             loss = mle + mse
         loss.backward()
         _rows.join(self.device)                      # encoder weight gradients forked to the side stream
+        _flow.join(self.device)                      # decoder parameter gradients (weight_norm backward)
         g = self.flat.grad
         if self.world > 1:
             dist.all_reduce(g)                       # the step's single collective

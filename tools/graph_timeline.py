@@ -22,15 +22,24 @@ g = GraphedTrainStep(step, host, warmup=1)
 for _ in range(3):
     g.run()
 torch.cuda.synchronize()
+n_rep = 2 if "--two" in sys.argv else 1
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    g.run()
+    for _ in range(n_rep):
+        g.run()
     torch.cuda.synchronize()
 path = os.path.join(tempfile.mkdtemp(), "t.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
 t0, t1 = ev[0]["ts"], max(e["ts"] + e["dur"] for e in ev)
-print("# one replay: %d device activities, span %.3f ms" % (len(ev), (t1 - t0) / 1e3))
+print("# %d replay(s): %d device activities, span %.3f ms" % (n_rep, len(ev), (t1 - t0) / 1e3))
+if n_rep == 2:
+    radam = [e for e in ev if "radam_kernel" in e["name"]]
+    if len(radam) == 2:
+        first_end = radam[0]["ts"] + radam[0]["dur"]
+        nxt = min(e["ts"] for e in ev if e["ts"] >= first_end)
+        print("replay period (radam to radam): %.3f ms; idle between the replays: %.3f ms" %
+              ((radam[1]["ts"] - radam[0]["ts"]) / 1e3, (nxt - first_end) / 1e3))
 streams = collections.defaultdict(list)
 for e in ev:
     streams[e["args"].get("stream", -1)].append(e)
@@ -63,3 +72,11 @@ for k, (n, d) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:28]:
 main = max(streams.values(), key=lambda es: sum(e["dur"] for e in es))
 marks = [(e["ts"] - t0, e["name"][:50]) for e in main if "mas_kernel" in e["name"] or "radam" in e["name"] or "wn_pack" in e["name"] or "wn_grad" in e["name"] or "sqnorm" in e["name"]]
 print("\nmarkers on the main stream (ms): " + "; ".join("%s @ %.3f" % (n, t / 1e3) for t, n in marks))
+
+if "--list" in sys.argv:
+    n = int(sys.argv[sys.argv.index("--list") + 1])
+    print("\nfirst %d activities (all streams): start us | dur us | gap to previous end us | stream | name" % n)
+    prev_end = t0
+    for e in ev[:n]:
+        print("%9.1f %7.1f %7.1f  %s  %s" % (e["ts"] - t0, e["dur"], e["ts"] - prev_end, e["args"].get("stream", -1), e["name"][:70]))
+        prev_end = max(prev_end, e["ts"] + e["dur"])

@@ -572,7 +572,7 @@ rpr_attn_fwd_mma_kernel(const AttnArgs a)
 
 // ---- tensor-core backward, query tiles: dPd = dO V^T (+ band), softmax backward, dS scratch,
 //      dQ = dS K (+ band), dwK, dwV.  Same tile shape and ownership as the forward kernel.
-constexpr size_t kMSmemBq = kMSmem + (size_t)kMQ * 16 * 4;
+constexpr size_t kMSmemBq = kMSmem + (size_t)kMQ * 16 * 4 + (size_t)kMQ * kMP * 2;
 
 __global__ void __launch_bounds__(kMThreads)
 rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
@@ -587,6 +587,7 @@ rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
     float *S = Wk + kAMaxRel * kAD;
     float *AR = S + kMQ * kMSP;                                          // dO.wV[r], then Pd on the band
     float *BS = AR + kMQ * 16;                                           // dS on the band
+    __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(BS + kMQ * 16); // q tile (dwK reduction)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = blockIdx.x * kMQ, h = blockIdx.y, b = blockIdx.z;
     const int len = a.lengths[b], T = a.T, nrel = 2 * a.window + 1, w = a.window;
@@ -594,6 +595,7 @@ rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
     const int TK = min(kMT, (len + 15) & ~15);
     const size_t off = (size_t)a.utt_off[b] * a.ld + h * kAD;
     load_rows_bf16(Ds, a.dout + off, a.ld, i0, kMQ, len, tid);
+    load_rows_bf16(Qs, a.q + off, a.ld, i0, kMQ, len, tid);
     load_rows_bf16(Ks, a.k + off, a.ld, 0, TK, len, tid);
     load_rows_bf16(Vs, a.v + off, a.ld, 0, TK, len, tid);
     for (int e = tid; e < 16 * kAD; e += kMThreads) {
@@ -627,43 +629,67 @@ rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
     __syncwarp();
     // rows: dP = dPd * keep/(1-p); dS = P (dP - sum_j dP P) * scale  (RPR_MHA.py:117-120 backward)
     const float inv_keep = 1.f / (1.f - a.drop_p);
-    for (int rr = 0; rr < 16; ++rr) {
-        const int i = m0 + rr, gi = i0 + i;
-        float *row = S + i * kMSP;
-        if (gi >= len) {
-            for (int j = lane; j < TK; j += 32) row[j] = 0.f;
-            if (lane < 16) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
-            continue;
-        }
-        const size_t base = ((size_t)(b * a.H + h) * T + gi) * T;
-        float dot = 0.f;
-        for (int j = lane; j < len; j += 32) {
-            const int r = j - gi + w;
-            float dp = row[j] + ((r >= 0 && r < nrel) ? AR[i * 16 + r] : 0.f);
-            if (seed != 0) dp = attn_keep(seed, base + j, a.drop_p) ? dp * inv_keep : 0.f;
-            row[j] = dp;
-            dot = fmaf(dp, a.probs[base + j], dot);
-        }
-        for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        __syncwarp();                                            // AR[i][*] has been consumed
-        for (int j = lane; j < len; j += 32) {
-            const float p = a.probs[base + j];
-            const float ds = p * (row[j] - dot) * a.scale;
-            row[j] = ds;
-            a.ds[base + j] = ds;
-            const int r = j - gi + w;
-            if (r >= 0 && r < nrel) {                            // keep the band of Pd and dS for dwV / dwK
-                float pd = p;
-                if (seed != 0) pd = attn_keep(seed, base + j, a.drop_p) ? p * inv_keep : 0.f;
-                AR[i * 16 + r] = pd;
-                BS[i * 16 + r] = ds;
+    constexpr int kPer = (kMT + 31) / 32;                        // probabilities of one row held by a lane
+    for (int rg = 0; rg < 16; rg += 4) {
+        // the probabilities of four rows first (independent global loads in flight together), then the rows
+        float pr[4][kPer];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gi = i0 + m0 + rg + u;
+            const size_t base = ((size_t)(b * a.H + h) * T + gi) * T;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int j = lane + 32 * k;
+                pr[u][k] = (gi < len && j < len) ? __ldg(a.probs + base + j) : 0.f;
             }
         }
-        if (lane < nrel) {                                       // band positions outside the sentence
-            const int j = gi + lane - w;
-            if (j < 0 || j >= len) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = m0 + rg + u, gi = i0 + i;
+            float *row = S + i * kMSP;
+            if (gi >= len) {
+                for (int j = lane; j < TK; j += 32) row[j] = 0.f;
+                if (lane < 16) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
+                continue;
+            }
+            const size_t base = ((size_t)(b * a.H + h) * T + gi) * T;
+            float dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < len) {
+                    const int r = j - gi + w;
+                    float dp = row[j] + ((r >= 0 && r < nrel) ? AR[i * 16 + r] : 0.f);
+                    if (seed != 0) dp = attn_keep(seed, base + j, a.drop_p) ? dp * inv_keep : 0.f;
+                    row[j] = dp;
+                    dot = fmaf(dp, pr[u][k], dot);
+                }
+            }
+            for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            __syncwarp();                                        // AR[i][*] has been consumed
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int j = lane + 32 * k;
+                if (j < len) {
+                    const float p = pr[u][k];
+                    const float ds = p * (row[j] - dot) * a.scale;
+                    row[j] = ds;
+                    a.ds[base + j] = ds;
+                    const int r = j - gi + w;
+                    if (r >= 0 && r < nrel) {                    // keep the band of Pd and dS for dwV / dwK
+                        float pd = p;
+                        if (seed != 0) pd = attn_keep(seed, base + j, a.drop_p) ? p * inv_keep : 0.f;
+                        AR[i * 16 + r] = pd;
+                        BS[i * 16 + r] = ds;
+                    }
+                }
+            }
+            if (lane < nrel) {                                   // band positions outside the sentence
+                const int j = gi + lane - w;
+                if (j < 0 || j >= len) { AR[i * 16 + lane] = 0.f; BS[i * 16 + lane] = 0.f; }
+            }
+            for (int j = len + lane; j < TK; j += 32) row[j] = 0.f;
         }
-        for (int j = len + lane; j < TK; j += 32) row[j] = 0.f;
     }
     __syncwarp();
     // dQ = dS K + band(dS, wK)
@@ -712,7 +738,7 @@ rpr_attn_bwd_q_mma_kernel(const AttnArgs a)
             const int gi = i0 + i;
             if (gi >= len) break;
             accv = fmaf(AR[i * 16 + r], __bfloat162float(Ds[i * kMP + d]), accv);
-            acck = fmaf(BS[i * 16 + r], __ldg(a.q + off + (size_t)gi * a.ld + d), acck);
+            acck = fmaf(BS[i * 16 + r], __bfloat162float(Qs[i * kMP + d]), acck);
         }
         atomicAdd(a.dwv + e, accv);
         atomicAdd(a.dwk + e, acck);

@@ -77,6 +77,8 @@ if "--list" in sys.argv:
     n = int(sys.argv[sys.argv.index("--list") + 1])
     print("\nfirst %d activities (all streams): start us | dur us | gap to previous end us | stream | name" % n)
     prev_end = t0
-    for e in ev[:n]:
+    start_ms = float(sys.argv[sys.argv.index("--from-ms") + 1]) if "--from-ms" in sys.argv else 0.0
+    sel = [e for e in ev if (e["ts"] - t0) / 1e3 >= start_ms]
+    for e in sel[:n]:
         print("%9.1f %7.1f %7.1f  %s  %s" % (e["ts"] - t0, e["dur"], e["ts"] - prev_end, e["args"].get("stream", -1), e["name"][:70]))
         prev_end = max(prev_end, e["ts"] + e["dur"])

@@ -578,6 +578,17 @@ class MLE_Loss(torch.nn.modules.loss._Loss):
         return loss + 0.5 * math.log(2 * math.pi)
 
 
+def _expand_by_path(mean, log_std, attentions, mel_masks):
+    """`mean @ attentions`, `log_Std @ attentions` (Modules.py:120-121).  The alignment is a 0/1 matrix with
+    exactly one 1 per valid mel frame, so the two dense [80,T_x]x[T_x,T_y] products (99 % zeros, SURVEY 8f
+    row 1) are a gather of token columns by frame -- and their backward a scatter-add -- with bit-identical
+    values: the product's only non-zero term is the gathered element."""
+    idx = attentions.argmax(dim=1)                                            # [B, T_y] token of each frame
+    both = torch.cat([mean, log_std], dim=1)                                   # [B, 160, T_x]
+    out = torch.gather(both, 2, idx.unsqueeze(1).expand(-1, both.shape[1], -1)) * mel_masks
+    return out[:, :mean.shape[1]], out[:, mean.shape[1]:]
+
+
 class GlowTTS(torch.nn.Module):
     """Modules.py:16-229 for Mode Vanilla and SE (LUT).  forward() returns the reference's
     8-tuple, inference() its 3-tuple."""
@@ -651,8 +662,7 @@ class GlowTTS(torch.nn.Module):
                      + (-0.5 * mean ** 2 * r).sum(dim=1).unsqueeze(-1))
             attentions = d["Maximum_Path_Generater"](log_p, None, t_len, m_len)
 
-        mel_mean = mean @ attentions
-        mel_log_std = log_std @ attentions
+        mel_mean, mel_log_std = _expand_by_path(mean, log_std, attentions, mel_masks)
         log_dur_targets = torch.log(attentions.sum(dim=-1).unsqueeze(1) + 1e-7) * token_masks
         return z, mel_mean, mel_log_std, log_dets, log_dur, log_dur_targets, attentions, None
 

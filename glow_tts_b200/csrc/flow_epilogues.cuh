@@ -107,6 +107,34 @@ template <int N> __device__ __forceinline__ void st_vec(__nv_bfloat16 *p, const 
     }
 }
 
+// read-only bf16 segment through the non-coherent path: the compiler may hoist it above earlier stores
+template <int N> __device__ __forceinline__ void ldg_vec(const __nv_bfloat16 *p, float (&v)[N])
+{
+    static_assert(N % 8 == 0, "ldg_vec: multiples of 8");
+#pragma unroll
+    for (int i = 0; i < N / 8; ++i) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        unpack_bf16x2(t.x, v[8 * i], v[8 * i + 1]); unpack_bf16x2(t.y, v[8 * i + 2], v[8 * i + 3]);
+        unpack_bf16x2(t.z, v[8 * i + 4], v[8 * i + 5]); unpack_bf16x2(t.w, v[8 * i + 6], v[8 * i + 7]);
+    }
+}
+template <int N> __device__ __forceinline__ void ldg_vec(const float *p, float (&v)[N])
+{
+    static_assert(N % 4 == 0, "ldg_vec: multiples of 4");
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+
+// read-only input segment: the non-coherent path when the width allows it, else a plain load
+template <int N, typename T> __device__ __forceinline__ void ld_ro(const T *p, float (&v)[N])
+{
+    if constexpr (N % (16 / sizeof(T)) == 0) ldg_vec<N>(p, v);
+    else ld_vec<N>(p, v);
+}
+
 template <bool FAST> __device__ __forceinline__ float tanh_t(float x)
 {
     if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -171,10 +199,20 @@ struct DropCfg {
     }
 };
 
+// Optional hook of the tcgen05 epilogue: called by each epilogue lane for (its row, a 32-column chunk it will
+// process) BEFORE the accumulator is ready, so that saved activations the functor reads (written a whole
+// forward pass ago, i.e. in DRAM) are on their way into L2 while the MMAs run:
+//     void prefetch32(int row, int n0) const;      (most functors: empty)
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ============================================================== forward ========
 // Start 1x1 (Modules.py:791): h0 = (W y_a + b) * mask
 template <typename ActT>
 struct EpiStart {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias; ActT *H; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
@@ -196,6 +234,7 @@ struct EpiStart {
 // packed columns are (tanh_c, sigmoid_c) pairs.
 template <typename ActT, bool FAST>
 struct EpiGate {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias; const float *spkb; ActT *TS; ActT *ACTS; const int32_t *row_utt; DropCfg drop;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
@@ -241,6 +280,7 @@ struct EpiGate {
 // Res/skip 1x1 (Modules.py:871-881): h' = (h + res) * mask ; skip accumulates; last layer -> out * mask
 template <typename ActT>
 struct EpiResSkip {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias; const ActT *Hin; ActT *Hout; float *SKIP; ActT *OUT; const int32_t *row_utt;
     int first, last;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
@@ -260,7 +300,7 @@ struct EpiResSkip {
             for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + b[j] + (first ? 0.f : old[j]) : 0.f;   // :881,:883
             st_vec<NV>(OUT + (size_t)row * kH + n0, out);
         } else if (n0 < kH) {
-            ld_vec<NV>(Hin + (size_t)row * kH + n0, old);
+            ld_ro<NV>(Hin + (size_t)row * kH + n0, old);
 #pragma unroll
             for (int j = 0; j < NV; ++j) out[j] = m ? old[j] + (v[j] + b[j]) : 0.f;                  // :878
             st_vec<NV>(Hout + (size_t)row * kH + n0, out);
@@ -283,6 +323,7 @@ __device__ __forceinline__ int group_channel(int g, int i) { return (i >> 1) * k
 // coupling and then THIS block's 4x4 mix and ActNorm.
 template <typename ActT, bool FAST>
 struct EpiEnd {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias;          // [160] interleaved
     const float *Y;             // this block's input  [rows][160] (fwd: post-mix y ; rev: block output z)
     float *OUTS;                // [rows][160] interleaved (mean, logs), or null
@@ -363,6 +404,7 @@ struct EpiEnd {
 // d(out) = d(outs) W_end, masked (WaveNet returns output * mask, Modules.py:883)
 template <typename ActT>
 struct EpiBwdEnd {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     ActT *DOUT; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
@@ -384,6 +426,13 @@ struct EpiBwdEnd {
 template <typename ActT>
 struct EpiBwdGate {
     const ActT *TS; ActT *DINS; ActT *DPRE; const int32_t *row_utt; DropCfg drop;
+    // the (tanh, sigmoid) pairs of this row chunk: 64 saved values = one 128 B line in bf16 (two in fp32)
+    __device__ __forceinline__ void prefetch32(int row, int n0) const
+    {
+        const ActT *p = TS + (size_t)row * kG + 2 * n0;
+        prefetch_l2(p);
+        if (sizeof(ActT) == 4) prefetch_l2(p + 32);
+    }
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         apply_u<NV>(row, row_utt[row], n0, v);
@@ -393,7 +442,7 @@ struct EpiBwdGate {
     {
         const bool m = utt >= 0;
         float ts[2 * NV], dins[2 * NV];
-        ld_vec<2 * NV>(TS + (size_t)row * kG + 2 * n0, ts);
+        ld_ro<2 * NV>(TS + (size_t)row * kG + 2 * n0, ts);          // saved in forward: read-only
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const float t = ts[2 * j], s = ts[2 * j + 1];
@@ -401,8 +450,16 @@ struct EpiBwdGate {
             dins[2 * j + 1] = m ? v[j] * t * s * (1.f - s) : 0.f;
         }
         if (DINS != nullptr) st_vec<2 * NV>(DINS + (size_t)row * kG + 2 * n0, dins);     // only the speaker bias reads it
+        if (drop.seed != 0) {                                  // uniform over the launch; same stream as EpiGate
+            const uint32_t t = drop.thresh(), s32 = drop.seed32(), i0 = drop.pair_index(row, 2 * n0);
+            const float sc = drop.scale();
 #pragma unroll
-        for (int j = 0; j < NV; ++j) drop.apply2(dins[2 * j], dins[2 * j + 1], row, 2 * (n0 + j));
+            for (int j = 0; j < NV; ++j) {
+                const uint32_t h = hash32((i0 + (uint32_t)j) * 0x9E3779B1u + s32);
+                dins[2 * j] = (h & 0xffffu) >= t ? dins[2 * j] * sc : 0.f;
+                dins[2 * j + 1] = (h >> 16) >= t ? dins[2 * j + 1] * sc : 0.f;
+            }
+        }
         st_vec<2 * NV>(DPRE + (size_t)row * kG + 2 * n0, dins);
     }
 };
@@ -410,6 +467,7 @@ struct EpiBwdGate {
 // d(h_i) = conv^T(d pre) + d(h_{i+1}) (residual, Modules.py:878), masked
 template <typename ActT>
 struct EpiBwdIn {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const ActT *DHnext; ActT *DH; const int32_t *row_utt;
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
@@ -421,7 +479,7 @@ struct EpiBwdIn {
         const bool m = utt >= 0;
         const size_t o = (size_t)row * kH + n0;
         float r[NV], out[NV];
-        if (DHnext != nullptr) ld_vec<NV>(DHnext + o, r);
+        if (DHnext != nullptr) ld_ro<NV>(DHnext + o, r);
 #pragma unroll
         for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + (DHnext != nullptr ? r[j] : 0.f) : 0.f;
         st_vec<NV>(DH + o, out);
@@ -430,6 +488,7 @@ struct EpiBwdIn {
 
 // d(y_a) += d(h0) W_start
 struct EpiBwdStart {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     float *DY;
     template <int NV> __device__ __forceinline__ void apply_u(int row, int, int n0, const float *v) const
     {

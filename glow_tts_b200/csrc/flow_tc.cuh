@@ -315,6 +315,7 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
             const int row_base = (item / NSL) * 128 + q * 32;
             const int n0 = (item % NSL) * BN;
             const int my_utt = row_utt[row_base + lane];               // one load per row; shuffled to its users below
+            for (int c0 = half * 32; c0 < BN; c0 += 64) epi.prefetch32(row_base + lane, n0 + c0);
             mbar_wait(&acc_full[acc], (it >> 1) & 1u);
             tc_fence_after();
             if (dbg && it < 2 && warp == 8 && lane == 0) dbg[11 + it * 8] = clock64();

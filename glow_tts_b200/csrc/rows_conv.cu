@@ -15,6 +15,7 @@ namespace glow {
 // y = mask * Dropout(ReLU?(acc + bias))   (bias null, no activation: data-gradient GEMM)
 // The dropout stream is the one glow_rows_act_backward replays (rows_norm.cu: RowsDrop).
 struct EpiRows {
+    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias; float *out; int ldo;
     int relu; float p; uint64_t seed; const uint64_t *step_dev;
     template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const

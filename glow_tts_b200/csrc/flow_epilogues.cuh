@@ -223,7 +223,7 @@ struct EpiStart {
     {
         const bool m = utt >= 0;
         float b[NV], out[NV];
-        ld_vec<NV>(bias + n0, b);
+        ld_ro<NV>(bias + n0, b);
 #pragma unroll
         for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + b[j] : 0.f;
         st_vec<NV>(H + (size_t)row * kH + n0, out);
@@ -245,7 +245,7 @@ struct EpiGate {
     {
         const bool m = utt >= 0;
         float pre[NV], ts[NV], acts[NV / 2];
-        ld_vec<NV>(bias + n0, pre);
+        ld_ro<NV>(bias + n0, pre);
 #pragma unroll
         for (int j = 0; j < NV; ++j) pre[j] += v[j];
         if (drop.seed != 0) {                                  // uniform over the launch
@@ -260,7 +260,7 @@ struct EpiGate {
         }
         if (spkb != nullptr) {                                 // uniform: SE mode
             float sv[NV];
-            ld_vec<NV>(spkb + (size_t)(m ? utt : 0) * kG + n0, sv);
+            ld_ro<NV>(spkb + (size_t)(m ? utt : 0) * kG + n0, sv);
 #pragma unroll
             for (int j = 0; j < NV; ++j) pre[j] += sv[j];
         }
@@ -293,7 +293,7 @@ struct EpiResSkip {
         // n0 is a multiple of NV and NV divides kH, so the NV columns lie on one side of the res | skip split
         const bool m = utt >= 0;
         float b[NV], out[NV], old[NV];
-        ld_vec<NV>(bias + n0, b);
+        ld_ro<NV>(bias + n0, b);
         if (last) {
             if (!first) ld_vec<NV>(SKIP + (size_t)row * kH + n0, old);
 #pragma unroll
@@ -345,9 +345,14 @@ struct EpiEnd {
         const int c0 = n0 >> 1;
         float za[NV / 2], zb[NV / 2], bs[NV], outs[NV], oa[NV / 2], ob[NV / 2];
         float ld = 0.f;
-        ld_vec<NV>(bias + n0, bs);
-        ld_vec<NV / 2>(Y + (size_t)row * kC + c0, za);
-        ld_vec<NV / 2>(Y + (size_t)row * kC + kCh + c0, zb);
+        ld_ro<NV>(bias + n0, bs);
+        if (!reverse) {                      // forward: Y is only read (the reverse direction updates it in place)
+            ld_ro<NV / 2>(Y + (size_t)row * kC + c0, za);
+            ld_ro<NV / 2>(Y + (size_t)row * kC + kCh + c0, zb);
+        } else {
+            ld_vec<NV / 2>(Y + (size_t)row * kC + c0, za);
+            ld_vec<NV / 2>(Y + (size_t)row * kC + kCh + c0, zb);
+        }
 #pragma unroll
         for (int j = 0; j < NV; ++j) outs[j] = v[j] + bs[j];
         if (OUTS != nullptr) st_vec<NV>(OUTS + (size_t)row * kC + n0, outs);
@@ -364,10 +369,19 @@ struct EpiEnd {
             }
         }
         if (rowld != nullptr && m) atomicAdd(rowld + row, ld);
+        // per-channel ActNorm terms and the 4x4 matrix as vector loads: group q's channels are c0 + 2q, + 1 of
+        // each half, so the NV/4 groups of this call cover [c0, c0 + NV/2) of both halves contiguously
+        float sa[NV / 2], sb[NV / 2], ba[NV / 2], bb[NV / 2], wm[16];
+        if (mix_w != nullptr) {
+            ld_ro<NV / 2>(mix_scale + c0, sa); ld_ro<NV / 2>(mix_scale + kCh + c0, sb);
+            ld_ro<NV / 2>(mix_bias + c0, ba);  ld_ro<NV / 2>(mix_bias + kCh + c0, bb);
+            ld_ro<16>(mix_w, wm);
+        }
 #pragma unroll
         for (int q = 0; q < NV / 4; ++q) {
-            const int g = (c0 >> 1) + q;
             float in[4] = {za[2 * q], za[2 * q + 1], zb[2 * q], zb[2 * q + 1]};
+            const float sc[4] = {sa[2 * q], sa[2 * q + 1], sb[2 * q], sb[2 * q + 1]};
+            const float bi[4] = {ba[2 * q], ba[2 * q + 1], bb[2 * q], bb[2 * q + 1]};
             float out[4];
             if (mix_w == nullptr) {
 #pragma unroll
@@ -375,19 +389,15 @@ struct EpiEnd {
             } else if (!reverse) {
                 float u[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ch = group_channel(g, i);
-                    u[i] = mix_bias[ch] + mix_scale[ch] * in[i];                         // :693
-                }
+                for (int i = 0; i < 4; ++i) u[i] = bi[i] + sc[i] * in[i];                                    // :693
 #pragma unroll
                 for (int o = 0; o < 4; ++o)
-                    out[o] = m ? mix_w[o * 4] * u[0] + mix_w[o * 4 + 1] * u[1] + mix_w[o * 4 + 2] * u[2] + mix_w[o * 4 + 3] * u[3] : 0.f;
+                    out[o] = m ? wm[o * 4] * u[0] + wm[o * 4 + 1] * u[1] + wm[o * 4 + 2] * u[2] + wm[o * 4 + 3] * u[3] : 0.f;
             } else {
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    const int ch = group_channel(g, o);
-                    const float u = mix_w[o * 4] * in[0] + mix_w[o * 4 + 1] * in[1] + mix_w[o * 4 + 2] * in[2] + mix_w[o * 4 + 3] * in[3];
-                    out[o] = m ? (u - mix_bias[ch]) / mix_scale[ch] : 0.f;               // :690
+                    const float u = wm[o * 4] * in[0] + wm[o * 4 + 1] * in[1] + wm[o * 4 + 2] * in[2] + wm[o * 4 + 3] * in[3];
+                    out[o] = m ? (u - bi[o]) / sc[o] : 0.f;                                                   // :690
                 }
             }
             oa[2 * q] = out[0]; oa[2 * q + 1] = out[1];

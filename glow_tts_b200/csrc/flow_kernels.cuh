@@ -91,7 +91,10 @@ int side_stream(SideStream **out);
 // cuBLAS weight-gradient GEMMs (flow_wgrad.cu), row-major:
 //   C[b][K][N] (ldc) = beta*C + A_b[rows,K]^T * D[rows,N],  A_b = A + b*strideA, C_b = C + b*strideC
 //   mode 0: fp32 operands and math; 1: bf16 operands; 2: fp32 operands, bf16 tensor-core math
+//   defer: the gradient may only be complete after the next wgrad_flush(st) on the same stream (split
+//   reductions of consecutive calls are summed in one launch)
 int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
-               float *C, int ldc, int batch, long long strideA, long long strideC, float beta);
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer = false);
+int wgrad_flush(cudaStream_t st);
 
 }  // namespace glow

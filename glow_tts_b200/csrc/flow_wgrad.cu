@@ -5,6 +5,7 @@
 //   m = N, n = K, k = rows, first operand D (ld = ldd), second operand A (ld = lda).
 #include <cublas_v2.h>
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 
 #include "flow_kernels.cuh"
@@ -59,13 +60,49 @@ int side_stream(SideStream **out)
 // tile down the whole row axis, i.e. 9 - 90 CTAs on 148 SMs.  Instead the row axis is cut into S
 // chunks that become extra batch entries (pointer-array batched GEMM into fp32 partials) and a small
 // kernel sums the S partials into C.
-struct SplitScratch {
-    float *partial;          // [S][taps][K][N] fp32
-    const void **ptrs;       // 3 x kMaxSplitBatch device pointers: A, D, C
-    size_t partial_floats;
-};
+//
+// Two things keep the bookkeeping off the critical path: the pointer arrays of a call site are built
+// once and cached (buffers keep their addresses from step to step), and the reductions of consecutive
+// GEMMs are DEFERRED into one launch (wgrad_flush: a decoder block's 13 gradients in one kernel).
 constexpr int kMaxSplitBatch = 96;
-constexpr size_t kSplitFloats = (size_t)4 * 5 * 192 * 384 + 1024;      // the largest case: S=4 x 5 taps x 192 x 384
+constexpr int kMaxSplitJobs = 16;
+constexpr int kSplitSlots = 1024;
+constexpr size_t kSplitFloats = (size_t)12 << 20;                       // 48 MB of fp32 partials (one decoder block: ~11 M)
+
+struct SplitJob {
+    const float *P; float *C;
+    int taps, S, K, N, ldc;
+    long long strideC, first;           // first: index of this job's first output element in the flush
+};
+struct SplitJobs {
+    int count;
+    long long total;
+    SplitJob job[kMaxSplitJobs];
+};
+struct SplitKey {
+    const void *A, *D; const float *P;
+    int taps, S, chunk, lda, ldd, K, N, mode;
+    long long strideA;
+    bool operator==(const SplitKey &o) const
+    {
+        return A == o.A && D == o.D && P == o.P && taps == o.taps && S == o.S && chunk == o.chunk && lda == o.lda &&
+               ldd == o.ldd && K == o.K && N == o.N && mode == o.mode && strideA == o.strideA;
+    }
+};
+struct SplitKeyHash {
+    size_t operator()(const SplitKey &k) const
+    {
+        size_t h = (size_t)k.A * 1000003u ^ (size_t)k.D * 998244353u ^ (size_t)k.P * 19260817u;
+        return h ^ ((size_t)k.S << 7) ^ ((size_t)k.taps << 3) ^ ((size_t)k.chunk << 13) ^ (size_t)k.strideA;
+    }
+};
+struct SplitScratch {
+    float *partial;                     // kSplitFloats fp32, handed out linearly between flushes
+    const void **ptrs;                  // kSplitSlots x 3 x kMaxSplitBatch device pointers (A, D, C per batch entry)
+    size_t used;
+    SplitJobs pending;
+    std::unordered_map<SplitKey, int, SplitKeyHash> *slots;
+};
 static SplitScratch g_split[16];
 static bool g_split_init[16] = {false};
 
@@ -77,9 +114,13 @@ static int split_scratch(SplitScratch **out)
     std::lock_guard<std::mutex> lock(g_handle_mu);
     if (!g_split_init[dev]) {
         SplitScratch &s = g_split[dev];
-        GLOW_CHECK_CUDA(cudaMalloc(&s.partial, kSplitFloats * sizeof(float)));     // once per device (not under capture:
-        GLOW_CHECK_CUDA(cudaMalloc(&s.ptrs, 3 * kMaxSplitBatch * sizeof(void *))); //  the first backward is a warm-up step)
-        s.partial_floats = kSplitFloats;
+        // once per device; never under stream capture (the first backward is an eager warm-up step)
+        GLOW_CHECK_CUDA(cudaMalloc(&s.partial, kSplitFloats * sizeof(float)));
+        GLOW_CHECK_CUDA(cudaMalloc(&s.ptrs, (size_t)kSplitSlots * 3 * kMaxSplitBatch * sizeof(void *)));
+        s.used = 0;
+        s.pending.count = 0;
+        s.pending.total = 0;
+        s.slots = new std::unordered_map<SplitKey, int, SplitKeyHash>();
         g_split_init[dev] = true;
     }
     *out = &g_split[dev];
@@ -97,20 +138,43 @@ __global__ void split_ptrs_kernel(const void **ptrs, const char *A, const char *
     ptrs[2 * kMaxSplitBatch + b] = P + (long long)b * kn;
 }
 
-// C[tap][k][n] (row pitch ldc, tap pitch strideC) = sum_s P[s][tap][k][n]
+// every pending job: C[tap][k][n] (row pitch ldc, tap pitch strideC) = sum_s P[s][tap][k][n]
 __global__ void __launch_bounds__(256)
-split_reduce_kernel(const float *__restrict__ P, float *__restrict__ C, int taps, int S, int K, int N, int ldc,
-                    long long strideC)
+split_reduce_kernel(const __grid_constant__ SplitJobs jobs)
 {
-    const long long kn = (long long)K * N, total = kn * taps;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < jobs.total; g += (long long)gridDim.x * 256) {
+        int j = 0;
+        while (j + 1 < jobs.count && g >= jobs.job[j + 1].first) ++j;
+        const SplitJob &J = jobs.job[j];
+        const long long i = g - J.first, kn = (long long)J.K * J.N;
         const int tap = (int)(i / kn);
         const long long r = i - tap * kn;
-        const int k = (int)(r / N), n = (int)(r - (long long)k * N);
+        const int k = (int)(r / J.N), n = (int)(r - (long long)k * J.N);
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += P[((long long)s * taps + tap) * kn + r];
-        C[tap * strideC + (long long)k * ldc + n] = acc;
+        for (int s = 0; s < J.S; ++s) acc += J.P[((long long)s * J.taps + tap) * kn + r];
+        J.C[tap * J.strideC + (long long)k * J.ldc + n] = acc;
     }
+}
+
+static int flush_locked(SplitScratch *sc, cudaStream_t st)
+{
+    if (sc->pending.count > 0) {
+        const long long blocks = (sc->pending.total + 255) / 256;
+        split_reduce_kernel<<<(int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs), 256, 0, st>>>(sc->pending);
+        GLOW_CHECK_LAUNCH("split_reduce_kernel");
+    }
+    sc->pending.count = 0;
+    sc->pending.total = 0;
+    sc->used = 0;
+    return GLOW_OK;
+}
+
+int wgrad_flush(cudaStream_t st)
+{
+    SplitScratch *sc = nullptr;
+    int rc = split_scratch(&sc);
+    if (rc != GLOW_OK) return rc;
+    return flush_locked(sc, st);
 }
 
 static int pick_split(int rows, int K, int N, int taps)
@@ -119,12 +183,12 @@ static int pick_split(int rows, int K, int N, int taps)
     const int tiles = ((K + 63) / 64) * ((N + 63) / 64) * taps;
     for (int S = 16; S >= 2; S >>= 1)
         if (rows % S == 0 && tiles * S <= 384 && taps * S <= kMaxSplitBatch &&
-            (size_t)S * taps * K * N <= kSplitFloats) return S;
+            (size_t)S * taps * K * N <= kSplitFloats / 2) return S;
     return 1;
 }
 
 int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
-               float *C, int ldc, int batch, long long strideA, long long strideC, float beta)
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer)
 {
     cublasHandle_t h;
     int rc = get_handle(&h);
@@ -143,22 +207,44 @@ int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D,
         SplitScratch *sc = nullptr;
         rc = split_scratch(&sc);
         if (rc != GLOW_OK) return rc;
+        const size_t need = (size_t)S * taps * K * N;
+        if (sc->pending.count == kMaxSplitJobs || sc->used + need > kSplitFloats) {
+            rc = flush_locked(sc, st);
+            if (rc != GLOW_OK) return rc;
+        }
+        float *P = sc->partial + sc->used;
+        sc->used += (need + 63) & ~(size_t)63;
         const int chunk = rows / S;
         const long long esz = mode == 1 ? 2 : 4;
-        split_ptrs_kernel<<<1, kMaxSplitBatch, 0, st>>>(sc->ptrs, (const char *)A, (const char *)D, sc->partial, taps, S,
-                                                         strideA * esz, (long long)chunk * lda * esz,
-                                                         (long long)chunk * ldd * esz, (long long)K * N);
-        GLOW_CHECK_LAUNCH("split_ptrs_kernel");
+        // pointer arrays of this call site: built once, then found by key (addresses are stable across steps)
+        SplitKey key{A, D, P, taps, S, chunk, lda, ldd, K, N, mode, strideA};
+        int slot;
+        auto it = sc->slots->find(key);
+        if (it != sc->slots->end()) {
+            slot = it->second;
+        } else {
+            GLOW_REQUIRE((int)sc->slots->size() < kSplitSlots, GLOW_ERR_UNSUPPORTED, "wgrad: more than %d split call sites",
+                         kSplitSlots);
+            slot = (int)sc->slots->size();
+            (*sc->slots)[key] = slot;
+            split_ptrs_kernel<<<1, kMaxSplitBatch, 0, st>>>(sc->ptrs + (size_t)slot * 3 * kMaxSplitBatch, (const char *)A,
+                                                             (const char *)D, P, taps, S, strideA * esz,
+                                                             (long long)chunk * lda * esz, (long long)chunk * ldd * esz,
+                                                             (long long)K * N);
+            GLOW_CHECK_LAUNCH("split_ptrs_kernel");
+        }
+        const void **ptrs = sc->ptrs + (size_t)slot * 3 * kMaxSplitBatch;
         const float zero = 0.f;
-        s = cublasGemmBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, K, chunk, &alpha, sc->ptrs + kMaxSplitBatch, in_t, ldd,
-                                sc->ptrs, in_t, lda, &zero, (void *const *)(sc->ptrs + 2 * kMaxSplitBatch), CUDA_R_32F, N,
-                                taps * S, comp, CUBLAS_GEMM_DEFAULT);
+        s = cublasGemmBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_T, N, K, chunk, &alpha, ptrs + kMaxSplitBatch, in_t, ldd, ptrs, in_t,
+                                lda, &zero, (void *const *)(ptrs + 2 * kMaxSplitBatch), CUDA_R_32F, N, taps * S, comp,
+                                CUBLAS_GEMM_DEFAULT);
         GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasGemmBatchedEx(rows=%d,K=%d,N=%d,S=%d) failed: %d",
                      rows, K, N, S, (int)s);
-        const long long total = (long long)K * N * taps;
-        split_reduce_kernel<<<(int)((total + 255) / 256 < 4 * kNumSMs ? (total + 255) / 256 : 4 * kNumSMs), 256, 0, st>>>(
-            sc->partial, C, taps, S, K, N, ldc, strideC);
-        GLOW_CHECK_LAUNCH("split_reduce_kernel");
+        SplitJob &J = sc->pending.job[sc->pending.count++];
+        J.P = P; J.C = C; J.taps = taps; J.S = S; J.K = K; J.N = N; J.ldc = ldc; J.strideC = strideC;
+        J.first = sc->pending.total;
+        sc->pending.total += (long long)K * N * taps;
+        if (!defer) return flush_locked(sc, st);
         return GLOW_OK;
     }
     if (batch <= 1) {

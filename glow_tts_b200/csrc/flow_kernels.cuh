@@ -94,7 +94,8 @@ int side_stream(SideStream **out);
 //   defer: the gradient may only be complete after the next wgrad_flush(st) on the same stream (split
 //   reductions of consecutive calls are summed in one launch)
 int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
-               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer = false);
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer = false,
+               bool stable = false);        // stable: A, D, C keep their addresses from step to step (cached workspaces)
 int wgrad_flush(cudaStream_t st);
 
 }  // namespace glow

@@ -262,25 +262,25 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
         GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
         // dW_end[192][160] = OUT^T DOUTS
-        GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f, true));
+        GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f, true, true));
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
             const int rs_n = last ? kH : kG;
             // dW_rs[192][rs_n]: res columns from d(h_{i+1}), skip columns from d(out)
             if (!last) {
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DH[i + 1], kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true));
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f, true));
+                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DH[i + 1], kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true, true));
+                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f, true, true));
             } else {
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true));
+                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true, true));
             }
             // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
             GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
-                                kTaps, kH, (long long)kH * kG, 0.f, true));
+                                kTaps, kH, (long long)kH * kG, 0.f, true, true));
         }
         if (kBf16) {
-            GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true));
+            GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
         } else {
-            GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true));
+            GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
         }
         GLOW_TRY(wgrad_flush(side));                       // the block's split reductions, one launch
         {   // every bias gradient of the block: column sums of the gradients the GEMMs above read (one launch)

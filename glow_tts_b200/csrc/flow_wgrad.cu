@@ -67,6 +67,7 @@ int side_stream(SideStream **out)
 constexpr int kMaxSplitBatch = 96;
 constexpr int kMaxSplitJobs = 16;
 constexpr int kSplitSlots = 1024;
+constexpr int kSplitTemp = 64;                                          // slots [0, kSplitTemp): refilled on every use
 constexpr size_t kSplitFloats = (size_t)12 << 20;                       // 48 MB of fp32 partials (one decoder block: ~11 M)
 
 struct SplitJob {
@@ -100,6 +101,7 @@ struct SplitScratch {
     float *partial;                     // kSplitFloats fp32, handed out linearly between flushes
     const void **ptrs;                  // kSplitSlots x 3 x kMaxSplitBatch device pointers (A, D, C per batch entry)
     size_t used;
+    int next_temp;
     SplitJobs pending;
     std::unordered_map<SplitKey, int, SplitKeyHash> *slots;
 };
@@ -118,6 +120,7 @@ static int split_scratch(SplitScratch **out)
         GLOW_CHECK_CUDA(cudaMalloc(&s.partial, kSplitFloats * sizeof(float)));
         GLOW_CHECK_CUDA(cudaMalloc(&s.ptrs, (size_t)kSplitSlots * 3 * kMaxSplitBatch * sizeof(void *)));
         s.used = 0;
+        s.next_temp = 0;
         s.pending.count = 0;
         s.pending.total = 0;
         s.slots = new std::unordered_map<SplitKey, int, SplitKeyHash>();
@@ -188,7 +191,7 @@ static int pick_split(int rows, int K, int N, int taps)
 }
 
 int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D, int ldd, int rows, int K, int N,
-               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer)
+               float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer, bool stable)
 {
     cublasHandle_t h;
     int rc = get_handle(&h);
@@ -216,17 +219,28 @@ int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D,
         sc->used += (need + 63) & ~(size_t)63;
         const int chunk = rows / S;
         const long long esz = mode == 1 ? 2 : 4;
-        // pointer arrays of this call site: built once, then found by key (addresses are stable across steps)
-        SplitKey key{A, D, P, taps, S, chunk, lda, ldd, K, N, mode, strideA};
+        // Pointer arrays.  Call sites whose operands keep their addresses from step to step (the decoder's
+        // cached workspaces) build them once and find them by key; others (the encoder's per-step tensors)
+        // refill one of kSplitTemp rotating slots on every call -- the fill is an ordinary launch in front
+        // of the GEMM on the same stream, so it is also re-run by a replayed CUDA graph.
         int slot;
-        auto it = sc->slots->find(key);
-        if (it != sc->slots->end()) {
-            slot = it->second;
+        bool fill = true;
+        if (stable) {
+            SplitKey key{A, D, P, taps, S, chunk, lda, ldd, K, N, mode, strideA};
+            auto it = sc->slots->find(key);
+            if (it != sc->slots->end()) {
+                slot = it->second;
+                fill = false;
+            } else {
+                if ((int)sc->slots->size() >= kSplitSlots - kSplitTemp) sc->slots->clear();     // shapes keep changing: start over
+                slot = kSplitTemp + (int)sc->slots->size();
+                (*sc->slots)[key] = slot;
+            }
         } else {
-            GLOW_REQUIRE((int)sc->slots->size() < kSplitSlots, GLOW_ERR_UNSUPPORTED, "wgrad: more than %d split call sites",
-                         kSplitSlots);
-            slot = (int)sc->slots->size();
-            (*sc->slots)[key] = slot;
+            slot = sc->next_temp;
+            sc->next_temp = (sc->next_temp + 1) % kSplitTemp;
+        }
+        if (fill) {
             split_ptrs_kernel<<<1, kMaxSplitBatch, 0, st>>>(sc->ptrs + (size_t)slot * 3 * kMaxSplitBatch, (const char *)A,
                                                              (const char *)D, P, taps, S, strideA * esz,
                                                              (long long)chunk * lda * esz, (long long)chunk * ldd * esz,

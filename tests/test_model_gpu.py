@@ -138,6 +138,29 @@ def test_graph_replays_draw_fresh_dropout_masks():
     assert max(losses) - min(losses) < 0.5 * abs(losses[0]), losses          # same weights, different masks
 
 
+def test_eager_training_with_changing_batch_geometry():
+    """Real data never repeats a batch geometry: every cache keyed on lengths / addresses (row maps,
+    workspaces, token rows, split-wgrad pointer arrays, device ints) has to cope with fresh keys each step,
+    eagerly, in bf16 training mode (dropout on), and the loss must keep falling on a repeated batch."""
+    import math
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep
+    from tests._util import synth_batch
+    model, sd, g, batch, mode = load_case("vanilla_small", "bf16")
+    model.train()
+    step = TrainStep(model, load_hparams(Mode=mode, Precision="bf16"), torch.device("cuda:0"))
+    geos = [([23, 17, 9], [140, 96, 50]), ([40, 31], [300, 222]), ([12, 12, 12, 12], [64, 64, 64, 64]),
+            ([55], [410]), ([23, 17, 9], [140, 96, 50]), ([33, 8, 21, 14, 29], [200, 52, 130, 88, 176])]
+    for i, (tls, mls) in enumerate(geos * 2):
+        loss = float(step.run(step.to_device(synth_batch(100 + i, tls, mls))))
+        assert math.isfinite(loss), (i, loss)
+    first = None
+    for _ in range(6):
+        loss = float(step.run(step.to_device(batch)))
+        first = loss if first is None else first
+    assert math.isfinite(loss) and loss < first
+
+
 def test_state_dict_roundtrip_and_cpu_is_refused():
     from glow_tts_b200 import _lib
     model, sd, g, batch, mode = load_case("vanilla_small", "fp32")

@@ -77,6 +77,7 @@ SIGNATURES = {
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_rows_conv_slab_elems": (_Z, [_I, _I, _I]),
     "glow_rows_conv_pack": (_I, [_PROWS, _P, _P, _P]),
+    "glow_rows_conv_pack_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "glow_rows_conv_forward": (_I, [_PROWS, _P, _P, _P, _P]),
     "glow_rows_conv_backward_data": (_I, [_PROWS, _P, _P, _P]),
     "glow_rows_conv_backward_weight": (_I, [_PROWS, _P, _P, _P, _P]),

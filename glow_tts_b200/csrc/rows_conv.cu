@@ -83,6 +83,34 @@ rows_wgrad_accum_kernel(const float *__restrict__ dwt, float *__restrict__ grad,
     }
 }
 
+// every encoder conv of a step in one launch (job table in the kernel parameters)
+constexpr int kMaxPackJobs = 48;
+struct RowsPackJob {
+    const float *w; __nv_bfloat16 *slab_w, *slab_wt;
+    int cout, cin, taps, bn_w, bn_wt, first;      // first: index of the job's first element in the launch
+};
+struct RowsPackJobs {
+    int count, total;
+    RowsPackJob job[kMaxPackJobs];
+};
+__global__ void __launch_bounds__(256)
+rows_pack_multi_kernel(const __grid_constant__ RowsPackJobs jobs)
+{
+    for (int g = blockIdx.x * 256 + threadIdx.x; g < jobs.total; g += gridDim.x * 256) {
+        int lo = 0, hi = jobs.count - 1;
+        while (lo < hi) {                          // last job with first <= g
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs.job[mid].first <= g) lo = mid; else hi = mid - 1;
+        }
+        const RowsPackJob &J = jobs.job[lo];
+        const int i = g - J.first;
+        const int tap = i % J.taps, k = (i / J.taps) % J.cin, n = i / (J.taps * J.cin);
+        const __nv_bfloat16 wb = __float2bfloat16(J.w[i]);
+        J.slab_w[((((size_t)(n / J.bn_w) * J.taps + tap) * (J.cin / 8) + k / 8) * J.bn_w + n % J.bn_w) * 8 + (k & 7)] = wb;
+        J.slab_wt[((((size_t)(k / J.bn_wt) * J.taps + tap) * (J.cout / 8) + n / 8) * J.bn_wt + k % J.bn_wt) * 8 + (n & 7)] = wb;
+    }
+}
+
 template <int N, int KP, int NP, int LD, int TAPS, int DIR>
 static int run_gemm(const float *a, const void *slab, const float *bias, float *out, const int32_t *row_utt, int rows_pad,
                     cudaStream_t st, const char *name, const glow_rows_conv_call *c = nullptr)
@@ -131,6 +159,28 @@ int glow_rows_conv_pack(const glow_rows_conv_call *c, const float *weight, void 
                        (cudaStream_t)c->stream>>>(weight, c->cout, c->cin, c->taps, rows_bn(c->cout), rows_bn(c->cin),
                                                   (__nv_bfloat16 *)slab_w, (__nv_bfloat16 *)slab_wt);
     GLOW_CHECK_LAUNCH("rows_pack_kernel");
+    return GLOW_OK;
+}
+
+int glow_rows_conv_pack_multi(int n, const int *shapes, const float *const *weights, void *const *slab_w,
+                              void *const *slab_wt, glow_stream_t stream)
+{
+    GLOW_REQUIRE(n >= 1 && n <= kMaxPackJobs && shapes && weights && slab_w && slab_wt, GLOW_ERR_INVALID,
+                 "rows_conv_pack_multi: n=%d (1..%d) or null pointer", n, kMaxPackJobs);
+    RowsPackJobs jobs;
+    jobs.count = n;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        const int cin = shapes[3 * i], cout = shapes[3 * i + 1], taps = shapes[3 * i + 2];
+        GLOW_REQUIRE(find_shape(cin, cout, taps) >= 0 && weights[i] && slab_w[i] && slab_wt[i], GLOW_ERR_UNSUPPORTED,
+                     "rows_conv_pack_multi: job %d: cin=%d cout=%d taps=%d", i, cin, cout, taps);
+        jobs.job[i] = RowsPackJob{weights[i], (__nv_bfloat16 *)slab_w[i], (__nv_bfloat16 *)slab_wt[i],
+                                  cout, cin, taps, rows_bn(cout), rows_bn(cin), total};
+        total += cin * cout * taps;
+    }
+    jobs.total = total;
+    rows_pack_multi_kernel<<<4 * kNumSMs, 256, 0, (cudaStream_t)stream>>>(jobs);
+    GLOW_CHECK_LAUNCH("rows_pack_multi_kernel");
     return GLOW_OK;
 }
 

@@ -505,6 +505,15 @@ class Encoder(torch.nn.Module):
         return (h.Channels == 192 and h.Prenet.Kernel_Size == 5 and h.Transformer.Conv.Kernel_Size == 3
                 and h.Transformer.Conv.Calc_Channels == 768 and self.mel_dim == 80)
 
+    def _packed_weights(self, dev):
+        pk = getattr(self, "_pk", None)
+        if pk is None or pk.buf.device != dev:
+            convs = [m for m in self.layer_Dict["Prenet"].modules() if isinstance(m, torch.nn.Conv1d)]
+            convs += [m for m in self.layer_Dict["Transformer"].modules() if isinstance(m, torch.nn.Conv1d)]
+            convs.append(self.layer_Dict["Project"])
+            pk = self._pk = _rows.PackedWeights(convs, dev)
+        return pk
+
     def _site_seed(self, site):
         """Dropout stream of one call site of this step (0 in eval); csrc kernels mix in the device step counter."""
         if not self.training:
@@ -521,6 +530,8 @@ class Encoder(torch.nn.Module):
         h = _hp().Encoder
         self._calls = getattr(self, "_calls", 0) + 1
         tr = _rows.token_rows(host_lengths, tokens.shape[1], dev)
+        pk = self._packed_weights(dev)
+        pk.pack()                                  # every conv weight of the encoder -> bf16 slab images, one launch
         tok = tokens.reshape(-1).index_select(0, tr.src_idx)
         x = d["Embedding"](tok) * (math.sqrt(self.channels) * tr.valid)
         pre = d["Prenet"]
@@ -529,21 +540,22 @@ class Encoder(torch.nn.Module):
         site = 0
         for i in range(pre.stacks):
             c = pre.layer_Dict["CLRD_%d" % i].layer_Dict
-            y = _rows.rows_conv(y, c["Conv"], tr, x_masked=True)
+            y = _rows.rows_conv(y, c["Conv"], tr, x_masked=True, packed=pk)
             site += 1
             y = _rows.rows_norm(y, None, c["LayerNorm"], tr, relu=True, p_out=p_pre, seed_out=self._site_seed(site))
-        x = _rows.rows_conv(y, pre.layer_Dict["Conv1x1"], tr, x_masked=True) + x
+        x = _rows.rows_conv(y, pre.layer_Dict["Conv1x1"], tr, x_masked=True, packed=pk) + x
         tf = d["Transformer"]
         p_tf = float(h.Transformer.Dropout_Rate)
         for i in range(tf.stacks):
             b = tf.layer_Dict["ANCRDCN_%d" % i].layer_Dict
-            a = b["Attention"].forward_rows(x, tr, lengths)
+            a = b["Attention"].forward_rows(x, tr, lengths, pk)
             y = _rows.rows_norm(a, x, b["LayerNorm_0"], tr, p_in=p_tf, seed_in=self._site_seed(site + 1))
-            f = _rows.rows_conv(y, b["Conv_0"], tr, relu=True, p=p_tf, seed=self._site_seed(site + 2), x_masked=True)
-            f = _rows.rows_conv(f, b["Conv_1"], tr, x_masked=True)
+            f = _rows.rows_conv(y, b["Conv_0"], tr, relu=True, p=p_tf, seed=self._site_seed(site + 2), x_masked=True,
+                                packed=pk)
+            f = _rows.rows_conv(f, b["Conv_1"], tr, x_masked=True, packed=pk)
             x = _rows.rows_norm(f, y, b["LayerNorm_1"], tr, p_in=p_tf, seed_in=self._site_seed(site + 3))
             site += 3
-        ms = tr.unpack(_rows.rows_conv(x, d["Project"], tr, x_masked=True)).transpose(1, 2)              # [B, 160, T]
+        ms = tr.unpack(_rows.rows_conv(x, d["Project"], tr, x_masked=True, packed=pk)).transpose(1, 2)              # [B, 160, T]
         mean, log_std = torch.split(ms, [self.mel_dim, self.mel_dim], dim=1)
         xd = tr.unpack(x.detach()).transpose(1, 2)                                        # == (x * mask).detach()
         spk = speakers.detach() if speakers is not None else None

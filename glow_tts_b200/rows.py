@@ -76,28 +76,70 @@ def _call(tr, cin, cout, taps, device, relu=False, p=0.0, seed=0):
     return c
 
 
+class PackedWeights:
+    """bf16 slab images of a set of Conv1d weights, refreshed by ONE kernel per step (pack())."""
+
+    def __init__(self, convs, device):
+        self.convs = list(convs)
+        L = _lib.lib()
+        sizes = []
+        for c in self.convs:
+            cout, cin, taps = c.weight.shape
+            n = L.glow_rows_conv_slab_elems(cin, cout, taps)
+            if n == 0:
+                raise _lib.GlowCoreError("rows_conv: no kernel built for cin=%d cout=%d taps=%d" % (cin, cout, taps))
+            sizes.append(n)
+        self.buf = torch.empty(2 * sum(sizes) + 64 * len(sizes), dtype=torch.bfloat16, device=device)
+        self.slabs, pos = {}, 0
+        for c, n in zip(self.convs, sizes):
+            w = self.buf[pos:pos + n]
+            pos += (n + 63) // 64 * 64
+            wt = self.buf[pos:pos + n]
+            pos += (n + 63) // 64 * 64
+            self.slabs[id(c)] = (w, wt)
+        k = len(self.convs)
+        self._shapes = (ctypes.c_int * (3 * k))(*[v for c in self.convs for v in (c.weight.shape[1], c.weight.shape[0],
+                                                                                  c.weight.shape[2])])
+        self._sw = (ctypes.c_void_p * k)(*[self.slabs[id(c)][0].data_ptr() for c in self.convs])
+        self._swt = (ctypes.c_void_p * k)(*[self.slabs[id(c)][1].data_ptr() for c in self.convs])
+
+    def pack(self):
+        dev = self.buf.device
+        k = len(self.convs)
+        w = (ctypes.c_void_p * k)(*[c.weight.data_ptr() for c in self.convs])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().glow_rows_conv_pack_multi(k, self._shapes, w, self._sw, self._swt, _lib.stream_ptr(dev)),
+                       "glow_rows_conv_pack_multi")
+
+    def get(self, conv):
+        return self.slabs.get(id(conv))
+
+
 class RowsConvFn(torch.autograd.Function):
     """y = mask * Dropout(ReLU?(bias + conv1d(mask * x))) on packed rows; weight in torch's Conv1d layout
     [cout, cin, taps].  seed == 0 disables the dropout (eval)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, tr, relu, p, seed):
+    def forward(ctx, x, weight, bias, tr, relu, p, seed, slabs=None):
         cout, cin, taps = weight.shape
         dev = x.device
         x = x.contiguous().float()
         L = _lib.lib()
-        n = L.glow_rows_conv_slab_elems(cin, cout, taps)
-        if n == 0:
-            raise _lib.GlowCoreError("rows_conv: no kernel built for cin=%d cout=%d taps=%d" % (cin, cout, taps))
-        slab_w = torch.empty(n, dtype=torch.bfloat16, device=dev)
-        slab_wt = torch.empty(n, dtype=torch.bfloat16, device=dev)
         y = torch.empty((tr.rows_pad, cout), dtype=torch.float32, device=dev)
         if not (p > 0 and seed):
             p, seed = 0.0, 0
         with torch.cuda.device(dev):
             call = _call(tr, cin, cout, taps, dev, relu, p, seed)
-            _lib.check(L.glow_rows_conv_pack(ctypes.byref(call), _lib.ptr(weight.detach().contiguous()),
-                                             _lib.ptr(slab_w), _lib.ptr(slab_wt)), "glow_rows_conv_pack")
+            if slabs is not None:                                  # packed once for the whole step (PackedWeights)
+                slab_w, slab_wt = slabs
+            else:
+                n = L.glow_rows_conv_slab_elems(cin, cout, taps)
+                if n == 0:
+                    raise _lib.GlowCoreError("rows_conv: no kernel built for cin=%d cout=%d taps=%d" % (cin, cout, taps))
+                slab_w = torch.empty(n, dtype=torch.bfloat16, device=dev)
+                slab_wt = torch.empty(n, dtype=torch.bfloat16, device=dev)
+                _lib.check(L.glow_rows_conv_pack(ctypes.byref(call), _lib.ptr(weight.detach().contiguous()),
+                                                 _lib.ptr(slab_w), _lib.ptr(slab_wt)), "glow_rows_conv_pack")
             _lib.check(L.glow_rows_conv_forward(ctypes.byref(call), _lib.ptr(x), _lib.ptr(slab_w),
                                                 _lib.ptr(bias.detach().contiguous()) if bias is not None else None,
                                                 _lib.ptr(y)), "glow_rows_conv_forward")
@@ -155,21 +197,23 @@ class RowsConvFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
-def rows_conv(x, conv, tr, relu=False, p=0.0, seed=0, x_masked=False):
+def rows_conv(x, conv, tr, relu=False, p=0.0, seed=0, x_masked=False, packed=None):
     """Apply a torch.nn.Conv1d's parameters to packed rows.  x_masked: the caller guarantees x is zero on
-    guard rows (every op of this module writes them as zeros), which saves a masking pass in backward."""
-    return _RowsConvApply.apply(x, conv.weight, conv.bias, tr, relu, p, seed, x_masked)
+    guard rows (every op of this module writes them as zeros), which saves a masking pass in backward.
+    packed: a PackedWeights whose pack() already ran this step (else the weight is packed here)."""
+    slabs = packed.get(conv) if packed is not None else None
+    return _RowsConvApply.apply(x, conv.weight, conv.bias, tr, relu, p, seed, x_masked, slabs)
 
 
 class _RowsConvApply(RowsConvFn):
     @staticmethod
-    def forward(ctx, x, weight, bias, tr, relu, p, seed, x_masked):
+    def forward(ctx, x, weight, bias, tr, relu, p, seed, x_masked, slabs):
         ctx.x_masked = bool(x_masked)
-        return RowsConvFn.forward(ctx, x, weight, bias, tr, relu, p, seed)
+        return RowsConvFn.forward(ctx, x, weight, bias, tr, relu, p, seed, slabs)
 
     @staticmethod
     def backward(ctx, dy):
-        return RowsConvFn.backward(ctx, dy) + (None,)
+        return RowsConvFn.backward(ctx, dy) + (None, None)
 
 
 class RowsNormFn(torch.autograd.Function):

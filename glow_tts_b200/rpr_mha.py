@@ -146,17 +146,17 @@ class RPR_Multihead_Attention(torch.nn.Module):
         self.weight_K = torch.nn.Parameter(torch.randn(1, n_rel, self.calc_channels_per_head) * std)
         self.weight_V = torch.nn.Parameter(torch.randn(1, n_rel, self.calc_channels_per_head) * std)
 
-    def forward_rows(self, x, tr, lengths):
+    def forward_rows(self, x, tr, lengths, packed=None):
         """Self-attention on packed token rows [rows, C] (rows.py): the four 1x1 convs run as tcgen05
         GEMMs over the rows, the attention core on [B, C, T] views of their outputs."""
         from . import rows as _rows
         d = self.layer_Dict
-        q, k, v = (_rows.rows_conv(x, d[n], tr, x_masked=True) for n in ("Query", "Key", "Value"))
+        q, k, v = (_rows.rows_conv(x, d[n], tr, x_masked=True, packed=packed) for n in ("Query", "Key", "Value"))
         seed = self._next_seed()
         lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
         out = _AttnRowsFn.apply(q, k, v, self.weight_K, self.weight_V, tr, lengths, self.num_heads,
                                 self.relative_postion_clipping_distance, self.dropout_rate, seed)
-        return _rows.rows_conv(out, d["Projection"], tr, x_masked=True)
+        return _rows.rows_conv(out, d["Projection"], tr, x_masked=True, packed=packed)
 
     def _next_seed(self):
         if not (self.training and self.dropout_rate > 0):

@@ -243,6 +243,10 @@ size_t glow_rows_conv_slab_elems(int cin, int cout, int taps);
 /* weight [cout, cin, taps] fp32 (torch Conv1d layout) -> slab_w (forward operand) and slab_wt
  * (data-gradient operand), each glow_rows_conv_slab_elems bf16 elements. */
 int glow_rows_conv_pack(const glow_rows_conv_call *call, const float *weight, void *slab_w, void *slab_wt);
+/* The same for n weights in ONE launch (all encoder convs of a step): shapes = n x (cin, cout, taps),
+ * host arrays of n device pointers each. */
+int glow_rows_conv_pack_multi(int n, const int *shapes, const float *const *weights, void *const *slab_w,
+                              void *const *slab_wt, glow_stream_t stream);
 /* y = mask * Dropout(ReLU?(bias + conv(mask * x))); bias may be NULL. */
 int glow_rows_conv_forward(const glow_rows_conv_call *call, const float *x, const void *slab_w,
                            const float *bias, float *y);

@@ -162,6 +162,7 @@ coupling_bwd_kernel(const float *__restrict__ DZ, const float *__restrict__ Y, c
 // One thread per (row, group); per-CTA partial sums go through shared memory, then atomics
 // into the (zeroed) dwpack slots an_scale (dlogs), an_bias, w.
 // ---------------------------------------------------------------------------
+constexpr int kMixRows = 64;           // rows per CTA of mix_bwd_kernel (grid = rows_pad / kMixRows)
 static __global__ void __launch_bounds__(256)
 mix_bwd_kernel(const float *__restrict__ DY, const float *__restrict__ Y, const int32_t *__restrict__ row_utt,
                int rows_pad, const float *__restrict__ wp, BlockPack bp, float *__restrict__ dwp,
@@ -173,40 +174,51 @@ mix_bwd_kernel(const float *__restrict__ DY, const float *__restrict__ Y, const 
     if (tid < 16) s_dw[tid] = 0.f;
     __syncthreads();
     const float *W = wp + bp.w, *Winv = wp + bp.winv, *scale = wp + bp.an_scale, *bias = wp + bp.an_bias;
-    // CTA covers 32 rows x 40 groups = 1280 items, 5 per thread; consecutive threads -> consecutive groups
-    const int row0 = blockIdx.x * 32;
-    float dw_loc[16];
+    // CTA covers kMixRows rows; thread -> one fixed channel group g (consecutive threads: consecutive groups,
+    // so a row is read contiguously) and every 6th row: the per-channel sums stay in registers until the end
+    constexpr int kGroups = kC / 4, kSlots = 240 / kGroups;          // 40 groups x 6 row slots = 240 active threads
+    const int row0 = blockIdx.x * kMixRows;
+    const int g = tid % kGroups, slot = tid / kGroups;
+    float dw_loc[16], dl[4], db[4], wv[16], wi[16], sc[4], bi[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dw_loc[i] = 0.f;
-    for (int e = tid; e < 32 * (kC / 4); e += 256) {
-        const int r = e / (kC / 4), g = e % (kC / 4);
-        const int row = row0 + r;
-        if (row >= rows_pad) continue;
-        const bool m = row_utt[row] >= 0;
-        float dy[4], y[4], u[4], du[4];
+    for (int i = 0; i < 16; ++i) { dw_loc[i] = 0.f; wv[i] = W[i]; wi[i] = Winv[i]; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ch = group_channel(g, i);
-            dy[i] = m ? DY[(size_t)row * kC + ch] : 0.f;
-            y[i] = Y[(size_t)row * kC + ch];
-        }
+    for (int i = 0; i < 4; ++i) { dl[i] = 0.f; db[i] = 0.f; sc[i] = scale[group_channel(g, i)]; bi[i] = bias[group_channel(g, i)]; }
+    if (slot < kSlots) {
+#pragma unroll 4
+        for (int r = slot; r < kMixRows; r += kSlots) {        // unrolled: the saved Y comes from DRAM, keep loads in flight
+            const int row = row0 + r;
+            if (row >= rows_pad) continue;
+            const bool m = row_utt[row] >= 0;
+            const float2 dya = *reinterpret_cast<const float2 *>(DY + (size_t)row * kC + 2 * g);
+            const float2 dyb = *reinterpret_cast<const float2 *>(DY + (size_t)row * kC + kCh + 2 * g);
+            const float2 ya = *reinterpret_cast<const float2 *>(Y + (size_t)row * kC + 2 * g);
+            const float2 yb = *reinterpret_cast<const float2 *>(Y + (size_t)row * kC + kCh + 2 * g);
+            const float dy[4] = {m ? dya.x : 0.f, m ? dya.y : 0.f, m ? dyb.x : 0.f, m ? dyb.y : 0.f};
+            const float y[4] = {ya.x, ya.y, yb.x, yb.y};
+            float u[4], du[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            u[i] = Winv[i * 4] * y[0] + Winv[i * 4 + 1] * y[1] + Winv[i * 4 + 2] * y[2] + Winv[i * 4 + 3] * y[3];
-            du[i] = W[i] * dy[0] + W[4 + i] * dy[1] + W[8 + i] * dy[2] + W[12 + i] * dy[3];
-        }
-#pragma unroll
-        for (int o = 0; o < 4; ++o)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dw_loc[o * 4 + i] += dy[o] * u[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ch = group_channel(g, i);
-            if (m) {
-                atomicAdd(&s_dlogs[ch], du[i] * (u[i] - bias[ch]));
-                atomicAdd(&s_dbias[ch], du[i]);
+            for (int i = 0; i < 4; ++i) {
+                u[i] = wi[i * 4] * y[0] + wi[i * 4 + 1] * y[1] + wi[i * 4 + 2] * y[2] + wi[i * 4 + 3] * y[3];
+                du[i] = wv[i] * dy[0] + wv[4 + i] * dy[1] + wv[8 + i] * dy[2] + wv[12 + i] * dy[3];
             }
-            if (DZ != nullptr) DZ[(size_t)row * kC + ch] = m ? du[i] * scale[ch] : 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dw_loc[o * 4 + i] += dy[o] * u[i];
+            if (m) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { dl[i] += du[i] * (u[i] - bi[i]); db[i] += du[i]; }
+            }
+            if (DZ != nullptr) {
+                *reinterpret_cast<float2 *>(DZ + (size_t)row * kC + 2 * g) = make_float2(m ? du[0] * sc[0] : 0.f, m ? du[1] * sc[1] : 0.f);
+                *reinterpret_cast<float2 *>(DZ + (size_t)row * kC + kCh + 2 * g) = make_float2(m ? du[2] * sc[2] : 0.f, m ? du[3] * sc[3] : 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(&s_dlogs[group_channel(g, i)], dl[i]);
+            atomicAdd(&s_dbias[group_channel(g, i)], db[i]);
         }
     }
 #pragma unroll

@@ -301,7 +301,7 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
         // ---- back on the main stream: 4x4 mix + ActNorm backward -> dz of the previous block
         const bool need_dz = k > 0 || dmel != nullptr;
-        mix_bwd_kernel<<<R / 32, 256, 0, c.st>>>(DY, b.Y, c.rows.row_utt, R, c.wpack + (size_t)k * c.bp.total, c.bp, dwp,
+        mix_bwd_kernel<<<R / kMixRows, 256, 0, c.st>>>(DY, b.Y, c.rows.row_utt, R, c.wpack + (size_t)k * c.bp.total, c.bp, dwp,
                                                 need_dz ? DZ : nullptr);
         GLOW_CHECK_LAUNCH("mix_bwd_kernel");
     }

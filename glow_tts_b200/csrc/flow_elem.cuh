@@ -97,12 +97,10 @@ static __global__ void logdet_finish_kernel(const float *__restrict__ rowld, con
     const int off = utt_off[b], len = utt_len[b];
     float s = 0.f;
     for (int r = lane; r < len; r += 32) s += rowld[off + r];
-    float konst = 0.f;
-    for (int k = 0; k < blocks; ++k) {
+    float konst = 0.f;                 // per frame: sum_k (sum(logs_k) + 40 * logdet(W_k)), both left by block_small_kernel
+    for (int k = lane; k < blocks; k += 32) {
         const float *wp = wpack + (size_t)k * pack_stride;
-        float sl = 0.f;
-        for (int c = lane; c < kC; c += 32) sl += logf(wp[bp.an_scale + c]);
-        konst += sl + (lane == 0 ? (float)(kC / 4) * wp[bp.logdet] : 0.f);
+        konst += wp[bp.logdet + 1] + (float)(kC / 4) * wp[bp.logdet];
     }
     s += konst * (float)len;
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -76,10 +76,16 @@ __global__ void block_small_kernel(const __grid_constant__ SmallJobs jobs, float
 {
     const int blk = blockIdx.x, tid = threadIdx.x;
     float *wp = wpack + (size_t)blk * pack_stride;
+    __shared__ float s_sumlogs;
+    if (tid == 0) s_sumlogs = 0.f;
+    __syncthreads();
     for (int c = tid; c < kC; c += blockDim.x) {
         wp[bp.an_scale + c] = expf(jobs.logs[blk][c]);
         wp[bp.an_bias + c] = jobs.bias[blk][c];
+        atomicAdd(&s_sumlogs, jobs.logs[blk][c]);
     }
+    __syncthreads();
+    if (tid == 0) wp[bp.logdet + 1] = s_sumlogs;      // sum of ActNorm logs: logdet_finish_kernel's per-frame constant
     if (tid == 0) {
         float a[4][4], inv[4][4];
         for (int i = 0; i < 4; ++i)

@@ -38,16 +38,23 @@ def test_attention_dropout_is_statistical_and_consistent():
     backward uses the same mask (finite-difference on a linear functional)."""
     model, sd, g, (tokens, tl, mels, ml, spk), mode = load_case("vanilla_small", "fp32")
     att = model.layer_Dict["Encoder"].layer_Dict["Transformer"].layer_Dict["ANCRDCN_0"].layer_Dict["Attention"]
-    att.train()
     x = torch.from_numpy(g["att_x"]).cuda()
-    _, a_train = att(queries=x, lengths=tl.cuda())
     att.eval()
     _, a_eval = att(queries=x, lengths=tl.cuda())
-    n = int(tl[0])
-    kept = (a_train[0, :, :n, :n] != 0).float().mean().item()
-    assert abs(kept - 0.9) < 0.02
-    nz = a_train[0, :, :n, :n] != 0
-    assert rel_err(a_train[0, :, :n, :n][nz], (a_eval[0, :, :n, :n] / 0.9)[nz]) < 1e-5
+    att.train()
+    # pool the valid cells of every utterance over several calls (each call draws a new mask) so the
+    # keep-rate bound is a 5-sigma one for the pooled sample instead of a fixed band on a few hundred cells
+    kept, cells = 0.0, 0
+    for _ in range(8):
+        _, a_train = att(queries=x, lengths=tl.cuda())
+        for b in range(x.shape[0]):
+            n = int(tl[b])
+            nz = a_train[b, :, :n, :n] != 0
+            kept += nz.float().sum().item()
+            cells += nz.numel()
+            assert rel_err(a_train[b, :, :n, :n][nz], (a_eval[b, :, :n, :n] / 0.9)[nz]) < 1e-5
+    sigma = (0.9 * 0.1 / cells) ** 0.5
+    assert abs(kept / cells - 0.9) < 5 * sigma + 1e-3, (kept / cells, cells)
 
 
 def test_rows_tensor_core_forward_matches_cuda_core_kernel():

@@ -82,6 +82,7 @@ int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, 
 // events per block parity.  Works under CUDA-graph capture (the event waits pull it into the capture).
 struct SideStream {
     cudaStream_t stream;
+    cudaStream_t enc_stream;             // the encoder's weight gradients: its backward overlaps the decoder's
     cudaEvent_t fork[2], done[2];        // decoder backward, per block parity
     cudaEvent_t enc_fork, enc_done;      // encoder weight gradients (rows_conv.cu)
     bool enc_pending;                    // enc_done has been recorded since the last glow_side_join

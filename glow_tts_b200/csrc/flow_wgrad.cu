@@ -13,19 +13,22 @@
 namespace glow {
 
 static std::mutex g_handle_mu;
-static cublasHandle_t g_handles[16] = {nullptr};
+static cublasHandle_t g_handles[16][2] = {{nullptr}};
 
-static int get_handle(cublasHandle_t *out)
+// lane 0: everything issued from the decoder's streams; lane 1: the encoder's side stream.  The two run
+// concurrently (the encoder's backward overlaps the decoder's), so each has its own handle (cuBLAS
+// workspace) and its own split scratch.
+static int get_handle(cublasHandle_t *out, int lane)
 {
     int dev = 0;
     GLOW_CHECK_CUDA(cudaGetDevice(&dev));
     GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
     std::lock_guard<std::mutex> lock(g_handle_mu);
-    if (g_handles[dev] == nullptr) {
-        cublasStatus_t s = cublasCreate(&g_handles[dev]);
+    if (g_handles[dev][lane] == nullptr) {
+        cublasStatus_t s = cublasCreate(&g_handles[dev][lane]);
         GLOW_REQUIRE(s == CUBLAS_STATUS_SUCCESS, GLOW_ERR_CUDA, "cublasCreate failed: %d", (int)s);
     }
-    *out = g_handles[dev];
+    *out = g_handles[dev][lane];
     return GLOW_OK;
 }
 
@@ -41,6 +44,7 @@ int side_stream(SideStream **out)
     if (!g_side_init[dev]) {
         SideStream &s = g_side[dev];
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.enc_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
@@ -105,17 +109,24 @@ struct SplitScratch {
     SplitJobs pending;
     std::unordered_map<SplitKey, int, SplitKeyHash> *slots;
 };
-static SplitScratch g_split[16];
-static bool g_split_init[16] = {false};
+static SplitScratch g_split[16][2];
+static bool g_split_init[16][2] = {{false}};
 
-static int split_scratch(SplitScratch **out)
+static int lane_of(cudaStream_t st)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
+    return (g_side_init[dev] && st == g_side[dev].enc_stream) ? 1 : 0;
+}
+
+static int split_scratch(SplitScratch **out, int lane)
 {
     int dev = 0;
     GLOW_CHECK_CUDA(cudaGetDevice(&dev));
     GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
     std::lock_guard<std::mutex> lock(g_handle_mu);
-    if (!g_split_init[dev]) {
-        SplitScratch &s = g_split[dev];
+    if (!g_split_init[dev][lane]) {
+        SplitScratch &s = g_split[dev][lane];
         // once per device; never under stream capture (the first backward is an eager warm-up step)
         GLOW_CHECK_CUDA(cudaMalloc(&s.partial, kSplitFloats * sizeof(float)));
         GLOW_CHECK_CUDA(cudaMalloc(&s.ptrs, (size_t)kSplitSlots * 3 * kMaxSplitBatch * sizeof(void *)));
@@ -124,9 +135,9 @@ static int split_scratch(SplitScratch **out)
         s.pending.count = 0;
         s.pending.total = 0;
         s.slots = new std::unordered_map<SplitKey, int, SplitKeyHash>();
-        g_split_init[dev] = true;
+        g_split_init[dev][lane] = true;
     }
-    *out = &g_split[dev];
+    *out = &g_split[dev][lane];
     return GLOW_OK;
 }
 
@@ -175,7 +186,7 @@ static int flush_locked(SplitScratch *sc, cudaStream_t st)
 int wgrad_flush(cudaStream_t st)
 {
     SplitScratch *sc = nullptr;
-    int rc = split_scratch(&sc);
+    int rc = split_scratch(&sc, lane_of(st));
     if (rc != GLOW_OK) return rc;
     return flush_locked(sc, st);
 }
@@ -194,7 +205,8 @@ int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D,
                float *C, int ldc, int batch, long long strideA, long long strideC, float beta, bool defer, bool stable)
 {
     cublasHandle_t h;
-    int rc = get_handle(&h);
+    const int lane = lane_of(st);
+    int rc = get_handle(&h, lane);
     if (rc != GLOW_OK) return rc;
     ProfScope prof("wgrad_cublas", st);
     cublasStatus_t s = cublasSetStream(h, st);
@@ -208,7 +220,7 @@ int wgrad_gemm(cudaStream_t st, int mode, const void *A, int lda, const void *D,
     const int S = (beta == 0.f && getenv("GLOW_WGRAD_NOSPLIT") == nullptr) ? pick_split(rows, K, N, taps) : 1;
     if (S > 1) {
         SplitScratch *sc = nullptr;
-        rc = split_scratch(&sc);
+        rc = split_scratch(&sc, lane);
         if (rc != GLOW_OK) return rc;
         const size_t need = (size_t)S * taps * K * N;
         if (sc->pending.count == kMaxSplitJobs || sc->used + need > kSplitFloats) {

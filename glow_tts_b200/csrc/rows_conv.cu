@@ -222,17 +222,26 @@ int glow_rows_conv_backward_weight(const glow_rows_conv_call *c, const float *x,
     int rc = check_rows(c, &shape);
     if (rc) return rc;
     GLOW_REQUIRE(x && dy && dw, GLOW_ERR_INVALID, "rows_conv_backward_weight: null pointer");
-    cudaStream_t st = (cudaStream_t)c->stream;
+    // Every encoder weight-gradient GEMM goes through the encoder side stream (one cuBLAS handle and one
+    // split scratch per lane, flow_wgrad.cu); here the caller's stream waits for the result right away.
+    SideStream *ss = nullptr;
+    rc = side_stream(&ss);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)c->stream, side = ss->enc_stream;
+    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, st));
+    GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
     const int center = (c->taps - 1) / 2;
     // dw[tap][cin][cout] = sum_r x[r + tap - center]^T dy[r]  (x, dy already zero on guard rows)
-    rc = wgrad_gemm(st, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout, dw,
+    rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout, dw,
                     c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
     if (rc) return rc;
     if (dbias != nullptr) {
-        GLOW_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, st));
-        colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, st>>>(dy, c->cout, c->rows_pad, c->cout, dbias);
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, side));
+        colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, side>>>(dy, c->cout, c->rows_pad, c->cout, dbias);
         GLOW_CHECK_LAUNCH("colsum_kernel");
     }
+    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, side));
+    GLOW_CHECK_CUDA(cudaStreamWaitEvent(st, ss->enc_fork, 0));
     return GLOW_OK;
 }
 
@@ -246,7 +255,7 @@ int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *c, const flo
     SideStream *ss = nullptr;
     rc = side_stream(&ss);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)c->stream, side = ss->stream;
+    cudaStream_t st = (cudaStream_t)c->stream, side = ss->enc_stream;
     GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, st));
     GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
     const int center = (c->taps - 1) / 2;

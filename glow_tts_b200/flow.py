@@ -73,6 +73,19 @@ def side_stream(device):
     return _SIDE[key]
 
 
+_ENC = {}
+
+
+def enc_stream(device):
+    """The text encoder's own stream: nothing in the encoder depends on the decoder (and vice versa) until
+    log_P, so training runs the two side by side, forward and -- because autograd replays every node on the
+    stream its forward ran on -- backward.  Fork / join with wait_stream, so it is capturable."""
+    key = str(torch.device(device))
+    if key not in _ENC:
+        _ENC[key] = torch.cuda.Stream(device)
+    return _ENC[key]
+
+
 def join(device):
     key = str(torch.device(device))
     if key in _SIDE_BUSY:

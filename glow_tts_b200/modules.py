@@ -15,6 +15,7 @@ PyTorch", BASELINE.json north_star).  There is no CPU fallback: tensors must be
 on a CUDA device.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -601,6 +602,11 @@ def _expand_by_path(mean, log_std, attentions, mel_masks):
     return out[:, :mean.shape[1]], out[:, mean.shape[1]:]
 
 
+# Training runs the text encoder on its own stream next to the decoder (flow.enc_stream); GLOW_ENC_OVERLAP=0
+# puts it back in front of the decoder on the caller's stream.
+ENCODER_OVERLAP = os.environ.get("GLOW_ENC_OVERLAP", "1") != "0"
+
+
 class GlowTTS(torch.nn.Module):
     """Modules.py:16-229 for Mode Vanilla and SE (LUT).  forward() returns the reference's
     8-tuple, inference() its 3-tuple."""
@@ -658,13 +664,23 @@ class GlowTTS(torch.nn.Module):
         dec = d["Decoder"]
         if torch.is_grad_enabled():
             dec.begin_prepare(dev)                 # weight_norm / slab images while the encoder runs
-        mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk, None,
-                                                           lengths=t_len, host_lengths=tl)
+        overlap = torch.is_grad_enabled() and ENCODER_OVERLAP
+        cur = torch.cuda.current_stream(dev)
+        enc = _flow.enc_stream(dev) if overlap else cur
+        if overlap:
+            enc.wait_stream(cur)
+        with torch.cuda.stream(enc):
+            mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk,
+                                                               None, lengths=t_len, host_lengths=tl)
         dec.host_lengths = ml
         try:
             z, log_dets, mel_masks = dec(mels[:, :, :max(ml)], mel_masks, spk, None, None)
         finally:
             dec.host_lengths = None
+        if overlap:
+            cur.wait_stream(enc)
+            for t in (mean, log_std, log_dur, token_masks):
+                t.record_stream(cur)           # allocated on the encoder's stream, consumed from here on
 
         with torch.no_grad():                                                    # Modules.py:107-116, fp32
             r = torch.exp(-2 * log_std)

@@ -64,6 +64,13 @@ SIGNATURES = {
     "glow_mas_workspace_bytes": (_Z, [_I, _I, _I]),
     "glow_mas_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _P, _Z, _P]),
     "glow_mas_forward_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _I]),
+    "glow_mas_align": (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _F, _P, _P, _P]),
+    "glow_align_logp": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "glow_align_expand_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "glow_align_expand_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "glow_mle_loss_workspace_floats": (_Z, []),
+    "glow_mle_loss_forward": (_I, [_P, _P, _P, _P, _P, _I, _Z, _I, _I, _P, _P, _P]),
+    "glow_mle_loss_backward": (_I, [_P, _P, _P, _P, _P, _I, _Z, _P, _P, _P, _P, _P]),
     "glow_flow_param_slots": (_I, [_PCFG]),
     "glow_flow_wpack_floats": (_Z, [_PCFG]),
     "glow_flow_wpack_tc_elems": (_Z, [_PCFG]),

@@ -74,7 +74,8 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
 
 // Build the per-tensor job table from the flat parameter buffer + host offset table.
 static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *off, float *grads,
-                       float *wpack, __nv_bfloat16 *wpack_tc, const float *dwpack, WnJobs *jobs, SmallJobs *small)
+                       float *wpack, __nv_bfloat16 *wpack_tc, const float *dwpack, WnJobs *jobs, SmallJobs *small,
+                       bool tc_only = false)
 {
     const bool se = cfg.spk_dim > 0;
     const int per_block = slots_per_block(se);
@@ -105,7 +106,8 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
         j.bn_w = has_tc ? slice_of(n_out) : n_out;
         j.bn_wt = has_tc ? slice_of(k_in) : k_in;
         j.cta_begin = cta;
-        cta += n_out;
+        j.skip_f32 = (tc_only && has_tc) ? 1 : 0;
+        cta += n_out / 8;
     };
     for (int k = 0; k < cfg.blocks; ++k) {
         const int64_t *o = off + (size_t)k * per_block;
@@ -184,7 +186,7 @@ int glow_flow_prepare(const glow_flow_config *cfg, const float *params, const in
     static thread_local WnJobs jobs;
     SmallJobs small{};
     build_jobs(fc, params, offsets_host, nullptr, wpack, precision != GLOW_F32 ? (__nv_bfloat16 *)wpack_tc : nullptr,
-               nullptr, &jobs, &small);
+               nullptr, &jobs, &small, precision == GLOW_BF16);
     const BlockPack bp = make_block_pack(cfg->spk_dim);
     rc = launch_block_small(small, wpack, bp.total, bp, (cudaStream_t)stream);
     if (rc) return rc;

@@ -17,7 +17,8 @@ struct WnJob {
     float *dv, *dg, *db;             // flat-gradient destinations (grad job)
     int n_out, k_in, taps, interleave;
     int bn_w, bn_wt;                 // column slice of the slabW (N = n_out) / slabWT (N = k_in) images
-    int cta_begin;
+    int cta_begin;                   // first CTA of this tensor; one CTA per 8 packed output channels
+    int skip_f32;                    // tcgen05 precision: W / WT (fp32) are never read, only the slabs and the bias
 };
 struct WnJobs {
     int count, total_ctas;

@@ -18,8 +18,10 @@ __device__ __forceinline__ int pack_col(int n, int n_out, bool interleave)
     return (n < half) ? 2 * n : 2 * (n - half) + 1;
 }
 
-// One CTA per output channel n.  v: [n_out][k_in][taps], g: [n_out] or null (plain conv).
-// Writes W[(tap*k_in + k)][n'] , WT[(tap*n_out + n')][k] fp32 and optional bf16 slab images
+// One CTA per group of 8 PACKED output channels np0 .. np0+7 (so every store below is a whole 16- or 32-byte
+// piece).  v: [n_out][k_in][taps], g: [n_out] or null (plain conv).
+// Writes W[(tap*k_in + k)][n'] , WT[(tap*n_out + n')][k] fp32 (unless skip_f32: the tcgen05 path never reads
+// them) and the bf16 slab images
 //   slabW [n_out/bn_w][tap][k_in/8][bn_w][8]    (B operand of the forward GEMM,  N = n_out, K = k_in)
 //   slabWT[k_in/bn_wt][tap][n_out/8][bn_wt][8]  (B operand of the data-grad GEMM, N = k_in, K = n_out)
 __device__ __forceinline__ const WnJob &find_job(const WnJobs &jobs, int cta)
@@ -32,40 +34,104 @@ __device__ __forceinline__ const WnJob &find_job(const WnJobs &jobs, int cta)
     return jobs.job[lo];
 }
 
-__global__ void __launch_bounds__(128)
+// reference output channel behind packed column np
+__device__ __forceinline__ int unpack_col(int np, int n_out, bool interleave)
+{
+    if (!interleave) return np;
+    return (np & 1) ? n_out / 2 + (np >> 1) : (np >> 1);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+
+constexpr int kWnGroup = 8;                    // packed channels per CTA
+constexpr int kWnMaxPer = kTaps * kH;          // 960 = the k=5 gate conv; every other tensor is smaller
+constexpr int kWnThreads = 256;
+constexpr int kWnIters = kWnMaxPer / 32;      // 30 elements of a channel row per lane
+constexpr int kWnBatch = 10;                  // loads in flight per lane in the read-modify-write of dv
+
+__global__ void __launch_bounds__(kWnThreads)
 wn_pack_kernel(const __grid_constant__ WnJobs jobs)
 {
     const WnJob &J = find_job(jobs, blockIdx.x);
     const float *__restrict__ v = J.v, *__restrict__ g = J.g, *__restrict__ bias = J.bias;
-    float *__restrict__ W = J.W, *__restrict__ WT = J.WT, *__restrict__ bpack = J.bpack;
+    float *__restrict__ W = J.skip_f32 ? nullptr : J.W, *__restrict__ WT = J.skip_f32 ? nullptr : J.WT;
+    float *__restrict__ bpack = J.bpack;
     __nv_bfloat16 *__restrict__ slabW = J.slabW, *__restrict__ slabWT = J.slabWT;
     const int n_out = J.n_out, k_in = J.k_in, taps = J.taps, interleave = J.interleave;
     const int bn_w = J.bn_w, bn_wt = J.bn_wt;
-    const int n = blockIdx.x - J.cta_begin, tid = threadIdx.x;
-    const int per = k_in * taps;
-    const float *vn = v + (size_t)n * per;
-    __shared__ float s_red[4];
-    float scale = 1.f;
-    if (g != nullptr) {
+    const int grp = blockIdx.x - J.cta_begin, np0 = grp * kWnGroup, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int per = k_in * taps, pitch = per + 1;
+    __shared__ float sw[kWnGroup * (kWnMaxPer + 1)];       // scaled weights, [channel][k*taps + tap]
+
+    {   // warp c: norm of channel c, scaled copy into shared memory (all of the row's loads in flight at once)
+        const int n = unpack_col(np0 + warp, n_out, interleave);
+        const float *vn = v + (size_t)n * per;
+        float *row = sw + warp * pitch;
+        float x[kWnIters];
         float ss = 0.f;
-        for (int i = tid; i < per; i += 128) ss += vn[i] * vn[i];
-        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if ((tid & 31) == 0) s_red[tid >> 5] = ss;
-        __syncthreads();
-        ss = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-        scale = g[n] / sqrtf(ss);
+#pragma unroll
+        for (int u = 0; u < kWnIters; ++u) {
+            const int i = lane + 32 * u;
+            x[u] = i < per ? vn[i] : 0.f;
+            ss += x[u] * x[u];
+        }
+        float scale = 1.f;
+        if (g != nullptr) {
+            for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            scale = g[n] / sqrtf(ss);
+        }
+#pragma unroll
+        for (int u = 0; u < kWnIters; ++u) {
+            const int i = lane + 32 * u;
+            if (i < per) row[i] = x[u] * scale;
+        }
+        if (lane == 0 && bias != nullptr) bpack[np0 + warp] = bias[n];
     }
-    const int np = pack_col(n, n_out, interleave);
-    if (tid == 0 && bias != nullptr) bpack[np] = bias[n];
-    for (int i = tid; i < per; i += 128) {
-        const int k = i / taps, tap = i % taps;
-        const float w = vn[i] * scale;
-        W[((size_t)tap * k_in + k) * n_out + np] = w;
-        if (WT != nullptr) WT[((size_t)tap * n_out + np) * k_in + k] = w;
+    __syncthreads();
+
+    // (tap, k) items, k fastest across threads: 8 packed channels side by side
+    for (int idx = tid; idx < per; idx += kWnThreads) {
+        const int tap = idx / k_in, k = idx - tap * k_in;
+        float w[kWnGroup];
+#pragma unroll
+        for (int c = 0; c < kWnGroup; ++c) w[c] = sw[c * pitch + k * taps + tap];
+        if (W != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(W + ((size_t)tap * k_in + k) * n_out + np0);     // 16-byte aligned:
+            dst[0] = make_float4(w[0], w[1], w[2], w[3]);                  // pack offsets, n_out and np0 are multiples of 4
+            dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+        }
+        if (slabWT != nullptr) {
+            uint4 q;
+            q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
+            q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
+            *reinterpret_cast<uint4 *>(slabWT + ((((size_t)(k / bn_wt) * taps + tap) * (n_out / 8) + grp) * bn_wt
+                                                 + k % bn_wt) * 8) = q;
+        }
+    }
+    // (tap, k/8, channel) items, channel fastest: 8 consecutive k of one channel
+    const int k8n = k_in / 8;
+    for (int idx = tid; idx < taps * k8n * kWnGroup; idx += kWnThreads) {
+        const int c = idx % kWnGroup, t2 = idx / kWnGroup;
+        const int k8 = t2 % k8n, tap = t2 / k8n;
+        const int np = np0 + c;
+        float w[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) w[kk] = sw[c * pitch + (k8 * 8 + kk) * taps + tap];
+        if (WT != nullptr) {
+            float4 *dst = reinterpret_cast<float4 *>(WT + ((size_t)tap * n_out + np) * k_in + k8 * 8);
+            dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+        }
         if (slabW != nullptr) {
-            const __nv_bfloat16 wb = __float2bfloat16(w);
-            slabW[((((size_t)(np / bn_w) * taps + tap) * (k_in / 8) + k / 8) * bn_w + np % bn_w) * 8 + (k & 7)] = wb;
-            slabWT[((((size_t)(k / bn_wt) * taps + tap) * (n_out / 8) + np / 8) * bn_wt + k % bn_wt) * 8 + (np & 7)] = wb;
+            uint4 q;
+            q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
+            q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
+            *reinterpret_cast<uint4 *>(slabW + ((((size_t)(np / bn_w) * taps + tap) * k8n + k8) * bn_w + np % bn_w) * 8) = q;
         }
     }
 }
@@ -125,7 +191,7 @@ __global__ void block_small_kernel(const __grid_constant__ SmallJobs jobs, float
 // Gradient of the weight-norm parametrisation.  One CTA per output channel:
 //   dW_eff[(tap*k+k)][n'] -> dg[n] += sum(dW*v)/||v|| ; dv += g/||v|| * (dW - v * sum(dW*v)/||v||^2)
 // plain (g == null): dv += dW.  Bias gradient: db[n] += dbpack[n'].
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kWnThreads)
 wn_grad_kernel(const __grid_constant__ WnJobs jobs)
 {
     const WnJob &J = find_job(jobs, blockIdx.x);
@@ -133,42 +199,82 @@ wn_grad_kernel(const __grid_constant__ WnJobs jobs)
     const float *__restrict__ dW = J.dW, *__restrict__ dbpack = J.dbpack;
     float *__restrict__ dv = J.dv, *__restrict__ dg = J.dg, *__restrict__ db = J.db;
     const int n_out = J.n_out, k_in = J.k_in, taps = J.taps, interleave = J.interleave;
-    const int n = blockIdx.x - J.cta_begin, tid = threadIdx.x;
-    const int per = k_in * taps;
-    const int np = pack_col(n, n_out, interleave);
+    const int grp = blockIdx.x - J.cta_begin, np0 = grp * kWnGroup, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int per = k_in * taps, pitch = per + 1;
+    __shared__ float sd[kWnGroup * (kWnMaxPer + 1)];       // dW of the group's channels, [channel][k*taps + tap]
+
+    // rows of dW[(tap*k_in + k)][n_out]: 8 adjacent packed channels = one 32-byte piece per row
+#pragma unroll 4
+    for (int idx = tid; idx < per; idx += kWnThreads) {
+        const int tap = idx / k_in, k = idx - tap * k_in;
+        const float4 *src = reinterpret_cast<const float4 *>(dW + ((size_t)tap * k_in + k) * n_out + np0);
+        const float4 lo = __ldg(src), hi = __ldg(src + 1);
+        float *dst = sd + k * taps + tap;
+        dst[0 * pitch] = lo.x; dst[1 * pitch] = lo.y; dst[2 * pitch] = lo.z; dst[3 * pitch] = lo.w;
+        dst[4 * pitch] = hi.x; dst[5 * pitch] = hi.y; dst[6 * pitch] = hi.z; dst[7 * pitch] = hi.w;
+    }
+    __syncthreads();
+
+    const int np = np0 + warp;
+    const int n = unpack_col(np, n_out, interleave);
     const float *vn = v + (size_t)n * per;
     float *dvn = dv + (size_t)n * per;
-    __shared__ float s_a[4], s_b[4];
-    if (tid == 0 && db != nullptr) db[n] += dbpack[np];
+    const float *row = sd + warp * pitch;
+    if (lane == 0 && db != nullptr) db[n] += dbpack[np];
+    // The row's loads are issued in explicit batches: dv may alias v as far as the compiler knows, so a plain
+    // loop would serialise load -> store -> load.
     if (g == nullptr) {
-        for (int i = tid; i < per; i += 128) {
-            const int k = i / taps, tap = i % taps;
-            dvn[i] += dW[((size_t)tap * k_in + k) * n_out + np];
+#pragma unroll
+        for (int b = 0; b < kWnIters; b += kWnBatch) {
+            float d[kWnBatch];
+#pragma unroll
+            for (int u = 0; u < kWnBatch; ++u) {
+                const int i = lane + 32 * (b + u);
+                d[u] = i < per ? dvn[i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kWnBatch; ++u) {
+                const int i = lane + 32 * (b + u);
+                if (i < per) dvn[i] = d[u] + row[i];
+            }
         }
         return;
     }
+    float x[kWnIters];
     float ss = 0.f, dot = 0.f;
-    for (int i = tid; i < per; i += 128) {
-        const int k = i / taps, tap = i % taps;
-        const float x = vn[i];
-        ss += x * x;
-        dot += x * dW[((size_t)tap * k_in + k) * n_out + np];
+#pragma unroll
+    for (int u = 0; u < kWnIters; ++u) {
+        const int i = lane + 32 * u;
+        x[u] = i < per ? vn[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kWnIters; ++u) {
+        const int i = lane + 32 * u;
+        ss += x[u] * x[u];
+        if (i < per) dot += x[u] * row[i];
     }
     for (int o = 16; o; o >>= 1) {
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
         dot += __shfl_xor_sync(0xffffffffu, dot, o);
     }
-    if ((tid & 31) == 0) { s_a[tid >> 5] = ss; s_b[tid >> 5] = dot; }
-    __syncthreads();
-    ss = s_a[0] + s_a[1] + s_a[2] + s_a[3];
-    dot = s_b[0] + s_b[1] + s_b[2] + s_b[3];
     const float inv_norm = rsqrtf(ss);
     const float gn = g[n];
-    if (tid == 0) dg[n] += dot * inv_norm;
+    if (lane == 0) dg[n] += dot * inv_norm;
     const float c1 = gn * inv_norm, c2 = gn * dot * inv_norm / ss;
-    for (int i = tid; i < per; i += 128) {
-        const int k = i / taps, tap = i % taps;
-        dvn[i] += c1 * dW[((size_t)tap * k_in + k) * n_out + np] - c2 * vn[i];
+#pragma unroll
+    for (int b = 0; b < kWnIters; b += kWnBatch) {
+        float d[kWnBatch];
+#pragma unroll
+        for (int u = 0; u < kWnBatch; ++u) {
+            const int i = lane + 32 * (b + u);
+            d[u] = i < per ? dvn[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kWnBatch; ++u) {
+            const int i = lane + 32 * (b + u);
+            if (i < per) dvn[i] = d[u] + c1 * row[i] - c2 * x[b + u];
+        }
     }
 }
 
@@ -195,15 +301,27 @@ __global__ void small_grad_kernel(const __grid_constant__ SmallJobs jobs, const 
 }
 
 // ------------------------------------------------------------------ launchers
+static int check_wn_jobs(const WnJobs &jobs)
+{
+    for (int i = 0; i < jobs.count; ++i) {
+        const WnJob &j = jobs.job[i];
+        GLOW_REQUIRE(j.n_out % kWnGroup == 0 && j.k_in % 8 == 0 && j.k_in * j.taps <= kWnMaxPer, GLOW_ERR_UNSUPPORTED,
+                     "weight_norm pack: tensor %d x %d x %d outside the supported shapes", j.n_out, j.k_in, j.taps);
+    }
+    return GLOW_OK;
+}
+
 int launch_wn_pack(const WnJobs &jobs, cudaStream_t st)
 {
-    wn_pack_kernel<<<jobs.total_ctas, 128, 0, st>>>(jobs);
+    if (int rc = check_wn_jobs(jobs)) return rc;
+    wn_pack_kernel<<<jobs.total_ctas, kWnThreads, 0, st>>>(jobs);
     GLOW_CHECK_LAUNCH("wn_pack_kernel");
     return GLOW_OK;
 }
 int launch_wn_grad(const WnJobs &jobs, cudaStream_t st)
 {
-    wn_grad_kernel<<<jobs.total_ctas, 128, 0, st>>>(jobs);
+    if (int rc = check_wn_jobs(jobs)) return rc;
+    wn_grad_kernel<<<jobs.total_ctas, kWnThreads, 0, st>>>(jobs);
     GLOW_CHECK_LAUNCH("wn_grad_kernel");
     return GLOW_OK;
 }

@@ -55,7 +55,8 @@ template <int E>
 __global__ void __launch_bounds__(kMasThreads)
 mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
            const int32_t *__restrict__ t_x, const int32_t *__restrict__ t_y,
-           int Tx, int Ty, uint32_t *__restrict__ path, uint32_t one_bits, float neg)
+           int Tx, int Ty, uint32_t *__restrict__ path, uint32_t one_bits, float neg,
+           int32_t *__restrict__ frame_token, int32_t *__restrict__ durations)
 {
     constexpr int P = 32 * E + 1;                 // pitch == 1 (mod 32): conflict-free both ways
     extern __shared__ __align__(16) unsigned char smem[];
@@ -96,6 +97,10 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
     const bool valid = tx >= 1 && ty >= 1 && tx <= ty && tx <= Tx && ty <= Ty && tx <= 32 * E;
     if (!valid) {                                   // outside the reference's defined behaviour
         zero_range(path_b, 0, plane, tid, kMasThreads);
+        if (frame_token != nullptr)
+            for (int y = tid; y < Ty; y += kMasThreads) frame_token[(size_t)b * Ty + y] = 0;
+        if (durations != nullptr)
+            for (int x = tid; x < Tx; x += kMasThreads) durations[(size_t)b * Tx + x] = 0;
         return;
     }
     const int ntiles = (ty + 31) >> 5;
@@ -180,11 +185,24 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
     __syncthreads();
     for (int y = tid; y < ty; y += kMasThreads)
         path_b[(size_t)pos[y] * Ty + y] = one_bits;   // core.pyx:33
+    // Optional by-products of the backtrack (glow_mas_align): the token of every frame and the number of
+    // frames of every token -- what `mean @ path` and `path.sum(-1)` (Modules.py:120-122) are made of.
+    if (frame_token != nullptr)
+        for (int y = tid; y < Ty; y += kMasThreads) frame_token[(size_t)b * Ty + y] = y < ty ? (int)pos[y] : 0;
+    if (durations != nullptr) {
+        int *cnt = reinterpret_cast<int *>(tiles);          // the value tiles are dead by now
+        for (int x = tid; x < Tx; x += kMasThreads) cnt[x] = 0;
+        __syncthreads();
+        for (int y = tid; y < ty; y += kMasThreads) atomicAdd(&cnt[pos[y]], 1);
+        __syncthreads();
+        for (int x = tid; x < Tx; x += kMasThreads) durations[(size_t)b * Tx + x] = cnt[x];
+    }
 }
 
 template <int E>
 static int launch_mas(const float *value, const float *mask, const int32_t *t_x, const int32_t *t_y,
-                      int B, int Tx, int Ty, uint32_t *path, uint32_t one_bits, float neg, cudaStream_t st)
+                      int B, int Tx, int Ty, uint32_t *path, uint32_t one_bits, float neg, cudaStream_t st,
+                      int32_t *frame_token = nullptr, int32_t *durations = nullptr)
 {
     const int ty_pad = (Ty + 31) & ~31;
     const size_t smem = sizeof(float) * 2 * 32 * (32 * E + 1) + (size_t)ty_pad * 33;
@@ -192,7 +210,7 @@ static int launch_mas(const float *value, const float *mask, const int32_t *t_x,
                  "mas: t_y_max=%d needs %zu B of shared memory (> 227 KB)", Ty, smem);
     GLOW_CHECK_CUDA(cudaFuncSetAttribute(mas_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof("mas", st);
-    mas_kernel<E><<<B, kMasThreads, smem, st>>>(value, mask, t_x, t_y, Tx, Ty, path, one_bits, neg);
+    mas_kernel<E><<<B, kMasThreads, smem, st>>>(value, mask, t_x, t_y, Tx, Ty, path, one_bits, neg, frame_token, durations);
     GLOW_CHECK_LAUNCH("mas_kernel");
     return GLOW_OK;
 }
@@ -203,9 +221,9 @@ extern "C" {
 
 size_t glow_mas_workspace_bytes(int, int, int) { return 0; }
 
-int glow_mas_forward(const float *value, const float *mask, const int32_t *t_x, const int32_t *t_y,
-                     int batch, int t_x_max, int t_y_max, void *path, int path_dtype, float max_neg_val,
-                     void *, size_t, glow_stream_t stream)
+static int mas_dispatch(const float *value, const float *mask, const int32_t *t_x, const int32_t *t_y,
+                        int batch, int t_x_max, int t_y_max, void *path, int path_dtype, float max_neg_val,
+                        int32_t *frame_token, int32_t *durations, glow_stream_t stream)
 {
     using namespace glow;
     GLOW_REQUIRE(batch >= 0 && t_x_max >= 0 && t_y_max >= 0, GLOW_ERR_INVALID, "mas: negative size");
@@ -220,11 +238,29 @@ int glow_mas_forward(const float *value, const float *mask, const int32_t *t_x, 
     const uint32_t one_bits = path_dtype == GLOW_F32 ? 0x3f800000u : 1u;
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *p = (uint32_t *)path;
-    if (t_x_max <= 32)  return launch_mas<1>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st);
-    if (t_x_max <= 96)  return launch_mas<3>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st);
-    if (t_x_max <= 160) return launch_mas<5>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st);
-    if (t_x_max <= 224) return launch_mas<7>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st);
-    return launch_mas<8>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st);
+    int32_t *ft = frame_token, *du = durations;
+    if (t_x_max <= 32)  return launch_mas<1>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st, ft, du);
+    if (t_x_max <= 96)  return launch_mas<3>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st, ft, du);
+    if (t_x_max <= 160) return launch_mas<5>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st, ft, du);
+    if (t_x_max <= 224) return launch_mas<7>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st, ft, du);
+    return launch_mas<8>(value, mask, t_x, t_y, batch, t_x_max, t_y_max, p, one_bits, max_neg_val, st, ft, du);
+}
+
+int glow_mas_forward(const float *value, const float *mask, const int32_t *t_x, const int32_t *t_y,
+                     int batch, int t_x_max, int t_y_max, void *path, int path_dtype, float max_neg_val,
+                     void *, size_t, glow_stream_t stream)
+{
+    return mas_dispatch(value, mask, t_x, t_y, batch, t_x_max, t_y_max, path, path_dtype, max_neg_val, nullptr, nullptr,
+                        stream);
+}
+
+int glow_mas_align(const float *value, const int32_t *t_x, const int32_t *t_y, int batch, int t_x_max, int t_y_max,
+                   void *path, int path_dtype, float max_neg_val, int32_t *frame_token, int32_t *durations,
+                   glow_stream_t stream)
+{
+    GLOW_REQUIRE(t_x && t_y && frame_token && durations, GLOW_ERR_INVALID, "mas_align: null pointer");
+    return mas_dispatch(value, nullptr, t_x, t_y, batch, t_x_max, t_y_max, path, path_dtype, max_neg_val, frame_token,
+                        durations, stream);
 }
 
 int glow_mas_forward_host(int32_t *paths, const float *values, const int32_t *t_xs, const int32_t *t_ys,

@@ -21,10 +21,10 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _lib, flow as _flow, rows as _rows
+from . import _lib, align as _align, flow as _flow, rows as _rows
 from .flat import FlatBuffer, offset_table
 from .hparams import load_hparams
-from .monotonic_align import maximum_path
+from .monotonic_align import maximum_path, maximum_path_align
 from .rpr_mha import RPR_Multihead_Attention
 
 hp = None
@@ -586,6 +586,8 @@ class MLE_Loss(torch.nn.modules.loss._Loss):
 
     def forward(self, z, mean, std, log_dets, lengths):
         h = _hp()
+        if FUSED_ALIGN and z.is_cuda and z.shape == mean.shape == std.shape:
+            return _align.mle_loss(z, mean, std, log_dets, lengths, h.Decoder.Num_Squeeze, h.Sound.Mel_Dim)
         loss = torch.sum(std) + 0.5 * torch.sum(torch.exp(-2 * std) * (z - mean) ** 2) - torch.sum(log_dets)
         loss = loss / (torch.sum(lengths // h.Decoder.Num_Squeeze) * h.Decoder.Num_Squeeze * h.Sound.Mel_Dim)
         return loss + 0.5 * math.log(2 * math.pi)
@@ -605,6 +607,8 @@ def _expand_by_path(mean, log_std, attentions, mel_masks):
 # Training runs the text encoder on its own stream next to the decoder (flow.enc_stream); GLOW_ENC_OVERLAP=0
 # puts it back in front of the decoder on the caller's stream.
 ENCODER_OVERLAP = os.environ.get("GLOW_ENC_OVERLAP", "1") != "0"
+# log_P / path expansion / MLE loss on the fused kernels of csrc/align.cu; GLOW_FUSED_ALIGN=0 keeps the framework ops.
+FUSED_ALIGN = os.environ.get("GLOW_FUSED_ALIGN", "1") != "0"
 
 
 class GlowTTS(torch.nn.Module):
@@ -682,17 +686,34 @@ class GlowTTS(torch.nn.Module):
             for t in (mean, log_std, log_dur, token_masks):
                 t.record_stream(cur)           # allocated on the encoder's stream, consumed from here on
 
-        with torch.no_grad():                                                    # Modules.py:107-116, fp32
-            r = torch.exp(-2 * log_std)
-            log_p = ((-0.5 * math.log(2 * math.pi) - log_std).sum(dim=1).unsqueeze(-1)
-                     + r.transpose(2, 1) @ (-0.5 * z ** 2)
-                     + (mean * r).transpose(2, 1) @ z
-                     + (-0.5 * mean ** 2 * r).sum(dim=1).unsqueeze(-1))
-            attentions = d["Maximum_Path_Generater"](log_p, None, t_len, m_len)
+        if FUSED_ALIGN:
+            # log_P, the search and the expansion by its path on csrc/align.cu + mas.cu.
+            # The fp32 parity mode keeps the reference's own expression for log_P (a differently ordered sum
+            # could flip a near-tie of the search); the rest is exact either way.
+            with torch.no_grad():
+                if dec.precision == "fp32":
+                    log_p = self._log_p(z, mean, log_std)
+                else:
+                    log_p = _align.log_p(z, mean, log_std, t_len, m_len)
+                attentions, frame_token, durations = maximum_path_align(log_p, t_len, m_len)
+            mel_mean, mel_log_std, log_dur_targets = _align.expand_by_path(mean, log_std, frame_token, durations,
+                                                                           t_len, m_len, z.shape[2])
+            return z, mel_mean, mel_log_std, log_dets, log_dur, log_dur_targets, attentions, None
 
+        with torch.no_grad():
+            attentions = d["Maximum_Path_Generater"](self._log_p(z, mean, log_std), None, t_len, m_len)
         mel_mean, mel_log_std = _expand_by_path(mean, log_std, attentions, mel_masks)
         log_dur_targets = torch.log(attentions.sum(dim=-1).unsqueeze(1) + 1e-7) * token_masks
         return z, mel_mean, mel_log_std, log_dets, log_dur, log_dur_targets, attentions, None
+
+    @staticmethod
+    def _log_p(z, mean, log_std):
+        """Modules.py:107-116 as the reference writes it (fp32)."""
+        r = torch.exp(-2 * log_std)
+        return ((-0.5 * math.log(2 * math.pi) - log_std).sum(dim=1).unsqueeze(-1)
+                + r.transpose(2, 1) @ (-0.5 * z ** 2)
+                + (mean * r).transpose(2, 1) @ z
+                + (-0.5 * mean ** 2 * r).sum(dim=1).unsqueeze(-1))
 
     @torch.no_grad()
     def inference(self, tokens, token_lengths, mels_for_prosody=None, mel_lengths_for_prosody=None, speakers=None,

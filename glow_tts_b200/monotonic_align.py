@@ -57,6 +57,29 @@ def maximum_path(value, mask=None, t_x=None, t_y=None, max_neg_val=-1e9, out_dty
     return path if path.dtype == want else path.to(want)
 
 
+def maximum_path_align(value, t_x, t_y, max_neg_val=-1e9):
+    """maximum_path plus what its backtrack knows anyway: -> (path f32 [B,T_x,T_y], frame_token i32 [B,T_y]
+    (row of the path in every column), durations i32 [B,T_x] (= path.sum(-1))).  t_x / t_y: device lengths."""
+    _lib.require_cuda(value, "value")
+    if value.dim() != 3:
+        raise ValueError("value must be [batch, t_x, t_y]")
+    v = value.detach()
+    if v.dtype != torch.float32:
+        v = v.float()
+    v = v.contiguous()
+    b, tx, ty = v.shape
+    t_x = t_x.to(device=v.device, dtype=torch.int32).contiguous()
+    t_y = t_y.to(device=v.device, dtype=torch.int32).contiguous()
+    path = torch.empty((b, tx, ty), dtype=torch.float32, device=v.device)
+    tok = torch.empty((b, ty), dtype=torch.int32, device=v.device)
+    dur = torch.empty((b, tx), dtype=torch.int32, device=v.device)
+    with torch.cuda.device(v.device):
+        rc = _lib.lib().glow_mas_align(_lib.ptr(v), _lib.ptr(t_x), _lib.ptr(t_y), b, tx, ty, _lib.ptr(path), _lib.GLOW_F32,
+                                       ctypes.c_float(max_neg_val), _lib.ptr(tok), _lib.ptr(dur), _lib.stream_ptr(v.device))
+    _lib.check(rc, "glow_mas_align")
+    return path, tok, dur
+
+
 def maximum_path_c(paths, values, t_xs, t_ys, max_neg_val=-1e9, device=0):
     """core.pyx:40 contract on host buffers: paths int32 [b,t_x,t_y] overwritten.
     Unlike the Cython core, `values` is left untouched (its mutation there is a

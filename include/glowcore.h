@@ -92,6 +92,83 @@ int glow_mas_forward_host(int32_t *paths, const float *values,
                           int batch, int t_x_max, int t_y_max,
                           float max_neg_val, int device);
 
+/*
+ * glow_mas_forward plus the two by-products of its backtrack that the caller's
+ * next lines are made of (Modules.py:120-122):
+ *   frame_token [batch, t_y_max] i32  row (token) of the path in every column
+ *                                     (0 for columns >= t_y[b])
+ *   durations   [batch, t_x_max] i32  path.sum(-1): frames assigned to a token
+ * t_x / t_y are required (device i32 [batch]).
+ */
+int glow_mas_align(const float *value, const int32_t *t_x, const int32_t *t_y,
+                   int batch, int t_x_max, int t_y_max,
+                   void *path, int path_dtype, float max_neg_val,
+                   int32_t *frame_token, int32_t *durations,
+                   glow_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Around the search: log_P producer, path expansion, MLE loss (fp32).
+ * replaces: Modules.py:107-116 (log_P), :120-122 (mean @ attentions,
+ *           log_Std @ attentions, log_Duration_Targets) and autograd's
+ *           backward of the two products; Modules.py:1020-1029 (MLE_Loss)
+ *           and its backward.
+ * ------------------------------------------------------------------------ */
+
+/*
+ * log_p[b,x,y] = sum_c(-log(2pi)/2 - s) + sum_c e (-z^2/2) + sum_c (m e) z
+ *                + sum_c(-m^2 e / 2),   e = exp(-2 s), s = log_std[b,c,x],
+ *                m = mean[b,c,x], z = z[b,c,y]       (Modules.py:108-115)
+ * z [batch, channels, ld_y], mean / log_std [batch, channels, ld_x] f32;
+ * log_p [batch, t_x_max, t_y_max] f32: ONLY the corner x < t_x[b], y < t_y[b]
+ * is written -- the part glow_mas_forward reads.
+ */
+int glow_align_logp(const float *z, const float *mean, const float *log_std,
+                    const int32_t *t_x, const int32_t *t_y,
+                    int batch, int channels, int t_x_max, int t_y_max,
+                    int ld_x, int ld_y, float *log_p, glow_stream_t stream);
+
+/*
+ * mel_mean[b,c,y] = mean[b,c,frame_token[b,y]] for y < t_y[b], else 0 (same
+ * for log_std -> mel_log_std): `mean @ attentions` with the 0/1 path, as a
+ * gather.  log_dur_targets [batch, t_x_max] (may be NULL) =
+ * log(durations + 1e-7) for x < t_x[b], else 0 (Modules.py:122).
+ * Outputs mel_* are [batch, channels, t_y_max].
+ */
+int glow_align_expand_forward(const float *mean, const float *log_std,
+                              const int32_t *frame_token, const int32_t *durations,
+                              const int32_t *t_x, const int32_t *t_y,
+                              int batch, int channels, int t_x_max, int t_y_max, int ld_x,
+                              float *mel_mean, float *mel_log_std, float *log_dur_targets,
+                              glow_stream_t stream);
+
+/* d_mean[b,c,x] = sum over the frames of token x of d_mel_mean[b,c,y] (same
+ * for log_std); d_mean / d_log_std are [batch, channels, ld_x], fully written. */
+int glow_align_expand_backward(const float *d_mel_mean, const float *d_mel_log_std,
+                               const int32_t *durations, const int32_t *t_x,
+                               int batch, int channels, int t_x_max, int t_y_max, int ld_x,
+                               float *d_mean, float *d_log_std, glow_stream_t stream);
+
+/* Floats of device workspace the MLE loss needs (forward writes, backward reads). */
+size_t glow_mle_loss_workspace_floats(void);
+
+/*
+ * loss[0] = (sum(s) + sum(exp(-2 s) (z - m)^2) / 2 - sum(log_dets)) / N + log(2pi)/2,
+ * N = sum(lengths // squeeze) * squeeze * mel_dim  (Modules.py:1024-1027).
+ * z, mean, log_std: `elems` f32 each (same shape, contiguous, 16-byte aligned);
+ * log_dets f32 [batch]; lengths i64 [batch] (device).
+ */
+int glow_mle_loss_forward(const float *z, const float *mean, const float *log_std,
+                          const float *log_dets, const int64_t *lengths,
+                          int batch, size_t elems, int squeeze, int mel_dim,
+                          float *workspace, float *loss, glow_stream_t stream);
+
+/* Gradients of that loss times grad_loss[0] (device scalar); workspace as left by the forward. */
+int glow_mle_loss_backward(const float *z, const float *mean, const float *log_std,
+                           const float *grad_loss, const float *workspace,
+                           int batch, size_t elems,
+                           float *d_z, float *d_mean, float *d_log_std, float *d_log_dets,
+                           glow_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * Flow decoder: Squeeze -> 12 x [ActNorm -> invertible 4x4 channel mix ->
  * affine coupling (Start 1x1, 4 x (k=5 gated conv, res/skip 1x1), End 1x1)]

@@ -52,6 +52,23 @@ align_logp_kernel(const float *__restrict__ z, const float *__restrict__ mean, c
         for (int j = 0; j < 8; ++j) { acc2[i][j] = 0.f; acc3[i][j] = 0.f; }
     float ca = 0.f, cb = 0.f;                            // this loader's share of the two per-token constants
 
+    // stage c0's operands are fetched into registers while stage c0 - 16 is being multiplied
+    float rs[4], rm[4], rz[8];
+    auto fetch = [&](int c0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + aq * 4 + u;
+            const bool ok = a_ok && c < C;
+            rs[u] = ok ? std_b[(size_t)c * ldx + x0 + ax] : 0.f;
+            rm[u] = ok ? mean_b[(size_t)c * ldx + x0 + ax] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + bq * 8 + u;
+            rz[u] = (b_ok && c < C) ? z_b[(size_t)c * ldy + y0 + by] : 0.f;
+        }
+    };
+    fetch(0);
     for (int c0 = 0; c0 < C; c0 += kLpC) {
         __syncthreads();
 #pragma unroll
@@ -59,7 +76,7 @@ align_logp_kernel(const float *__restrict__ z, const float *__restrict__ mean, c
             const int cl = aq * 4 + u, c = c0 + cl;
             float e = 0.f, me = 0.f;
             if (a_ok && c < C) {
-                const float s = std_b[(size_t)c * ldx + x0 + ax], m = mean_b[(size_t)c * ldx + x0 + ax];
+                const float s = rs[u], m = rm[u];
                 e = expf(-2.f * s);
                 me = m * e;
                 ca += -0.9189385332046727f - s;          // -log(2 pi) / 2 - log_Std   (Modules.py:108)
@@ -70,12 +87,13 @@ align_logp_kernel(const float *__restrict__ z, const float *__restrict__ mean, c
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int cl = bq * 8 + u, c = c0 + cl;
-            const float v = (b_ok && c < C) ? z_b[(size_t)c * ldy + y0 + by] : 0.f;
+            const int cl = bq * 8 + u;
+            const float v = rz[u];
             sZZ[cl][by] = -0.5f * (v * v);
             sZ[cl][by] = v;
         }
         __syncthreads();
+        if (c0 + kLpC < C) fetch(c0 + kLpC);
 #pragma unroll
         for (int cl = 0; cl < kLpC; ++cl) {
             const float4 e4 = *reinterpret_cast<const float4 *>(&sE[cl][ix * 4]);
@@ -164,13 +182,18 @@ align_expand_bwd_kernel(const float *__restrict__ g_mean, const float *__restric
         }
         if (tid == 0) s_start[Tx] = carry;
     }
-    __syncthreads();
+    // both gradient rows of this (utterance, channel) into shared memory, coalesced; then one thread per token
+    // sums its run from there (a dependent chain of ~6 shared-memory reads instead of global ones)
+    extern __shared__ float s_rows[];
+    float *sm = s_rows, *ss = s_rows + Ty;
     const float *gm = g_mean + ((size_t)b * C + c) * Ty, *gs = g_std + ((size_t)b * C + c) * Ty;
+    for (int y = tid; y < Ty; y += 256) { sm[y] = gm[y]; ss[y] = gs[y]; }
+    __syncthreads();
     for (int x = tid; x < ldx; x += 256) {
         float am = 0.f, as = 0.f;
         if (x < tx) {
             const int y0 = s_start[x], y1 = min(s_start[x + 1], Ty);
-            for (int y = y0; y < y1; ++y) { am += gm[y]; as += gs[y]; }
+            for (int y = y0; y < y1; ++y) { am += sm[y]; as += ss[y]; }
         }
         d_mean[((size_t)b * C + c) * ldx + x] = am;
         d_std[((size_t)b * C + c) * ldx + x] = as;
@@ -327,7 +350,11 @@ int glow_align_expand_backward(const float *d_mel_mean, const float *d_mel_log_s
                  "align_expand_backward: null pointer");
     GLOW_REQUIRE(t_x_max <= 256 && ld_x >= t_x_max && batch <= 65535, GLOW_ERR_UNSUPPORTED,
                  "align_expand_backward: t_x_max=%d > 256 or bad ld_x", t_x_max);
-    align_expand_bwd_kernel<<<dim3(channels, batch), 256, 0, (cudaStream_t)stream>>>(d_mel_mean, d_mel_log_std, durations, t_x,
+    const size_t smem = sizeof(float) * 2 * (size_t)t_y_max;
+    GLOW_REQUIRE(smem <= 200 * 1024, GLOW_ERR_UNSUPPORTED, "align_expand_backward: t_y_max=%d too long", t_y_max);
+    if (smem > 48 * 1024)
+        GLOW_CHECK_CUDA(cudaFuncSetAttribute(align_expand_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    align_expand_bwd_kernel<<<dim3(channels, batch), 256, smem, (cudaStream_t)stream>>>(d_mel_mean, d_mel_log_std, durations, t_x,
                                                                                  channels, t_x_max, t_y_max, ld_x, d_mean,
                                                                                  d_log_std);
     GLOW_CHECK_LAUNCH("align_expand_bwd_kernel");

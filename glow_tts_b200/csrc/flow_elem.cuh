@@ -259,6 +259,19 @@ colsum_kernel(const T *__restrict__ D, int ld, int rows, int N, float *__restric
 // result to up to four destinations (d(out) feeds the skip half of three Res_Skip biases and the whole
 // fourth).  grid = (row chunks of 128, jobs), 192 threads, each owning two adjacent columns (4 B / 8 B
 // loads, a row is read as one contiguous run).
+// zero a few element ranges of every block's slice of a [blocks][stride] fp32 buffer (grid: x = helpers, y = block)
+struct ZeroRanges {
+    int count;
+    size_t off[24], len[24];
+};
+static __global__ void __launch_bounds__(256)
+zero_ranges_kernel(float *__restrict__ base, size_t stride, const __grid_constant__ ZeroRanges r)
+{
+    float *p = base + (size_t)blockIdx.y * stride;
+    for (int i = 0; i < r.count; ++i)
+        for (size_t j = (size_t)blockIdx.x * 256 + threadIdx.x; j < r.len[i]; j += (size_t)gridDim.x * 256) p[r.off[i] + j] = 0.f;
+}
+
 constexpr int kMaxColsumJobs = 12;
 template <typename T>
 struct ColsumJobs {

@@ -222,7 +222,21 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
     SideStream *ss = nullptr;
     GLOW_TRY(side_stream(&ss));
     cudaStream_t side = ss->stream;
-    GLOW_CHECK_CUDA(cudaMemsetAsync(dwpack, 0, sizeof(float) * c.bp.total * c.cfg.blocks, c.st));
+    {   // zero what the backward ACCUMULATES into (ActNorm / 4x4 / bias / speaker gradients); the big W regions are
+        // overwritten by the weight-gradient GEMMs (beta = 0) and the W^T regions are never read -- clearing all of
+        // dwpack was a 170 MB memset in front of the first data-gradient kernel
+        ZeroRanges zr{};
+        auto add_range = [&](size_t off, size_t n) { zr.off[zr.count] = off; zr.len[zr.count] = n; ++zr.count; };
+        add_range(0, c.bp.start_w);
+        for (int i = 0; i < kLayers; ++i) {
+            add_range(c.bp.in_b[i], kG);
+            add_range(c.bp.rs_b[i], i < kLayers - 1 ? kG : kH);
+            if (c.cfg.spk_dim > 0) { add_range(c.bp.spk_b[i], kG); add_range(c.bp.spk_w[i], (size_t)c.cfg.spk_dim * kG); }
+        }
+        add_range(c.bp.end_b, kC);
+        zero_ranges_kernel<<<dim3(8, c.cfg.blocks), 256, 0, c.st>>>(dwpack, c.bp.total, zr);
+        GLOW_CHECK_LAUNCH("zero_ranges_kernel");
+    }
     pack_rows_kernel<float><<<R / 32, 256, 0, c.st>>>(dz, T, c.rows, DZ, (float *)nullptr, nullptr, nullptr, nullptr);
     GLOW_CHECK_LAUNCH("pack_rows_kernel");
     const int G2 = kGuard;                       // wgrad GEMMs skip the leading/trailing guard rows

@@ -116,7 +116,7 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
         const int col = y0 + lane;
         const bool colok = col < ty;
         const float *src = val_b + col;
-        constexpr int U = 8;
+        constexpr int U = 16;     // rows in flight per loader warp: at B = 32 only 32 SMs run, the loaders are latency-bound
         for (int x = xlo + (warp - 1); x < xhi; x += kMasLoaderWarps * U) {
             float v[U];
 #pragma unroll

@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     return 0
 
 
@@ -418,9 +418,25 @@ def run_own(args):
         "clocks": clocks, "roofline": roof, "roofline_hbm_decoder": hbm, "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     _finish(world, graphed)
     return 0
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON: keep the real stdout for it and point fd 1 at stderr for
+    everything else that may print there (NCCL's version banner, library warnings)."""
+    if getattr(sys, "_glow_json_fd", None) is None:       # on `sys`: tools/bench_extra imports this file a second time
+        sys.stdout.flush()
+        sys._glow_json_fd = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    fd = getattr(sys, "_glow_json_fd", None)
+    os.write(fd if fd is not None else 1, data)
 
 
 def _finish(world, graphed):
@@ -442,7 +458,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "mas", "decoder"])
+    ap.add_argument("--workload", default="train", choices=["train", "mas", "decoder", "inference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the cpu_baseline sample")
@@ -453,6 +469,7 @@ def main():
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: exactly --warmup warm-up steps, then --steps steps, nothing else")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload != "train":

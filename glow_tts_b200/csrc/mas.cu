@@ -141,18 +141,27 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
     for (int t = 0; t < ntiles; ++t) {
         __syncthreads();                            // tile t landed; tile t-1 consumed
         if (warp == 0) {
-            const float *buf = tiles + (t & 1) * 32 * P;
+            const float *buf = tiles + (t & 1) * 32 * P + lane * E;
             const int cend = min(32, ty - (t << 5));
+            // the column's values are read one column ahead: the loads do not depend on the DP chain, but issued
+            // inside it they would add a shared-memory latency to every one of the T_y serial steps
+            float vnext[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) vnext[j] = buf[j];
             for (int c = 0; c < cend; ++c) {
                 const int y = (t << 5) + c;
                 const int lo = max(0, tx + y - ty);
                 const int hi = min(tx, y + 1);
                 const float up = __shfl_up_sync(0xffffffffu, V[E - 1], 1);
+                float vcur[E];
+                const int cn = min(c + 1, 31);
+#pragma unroll
+                for (int j = 0; j < E; ++j) { vcur[j] = vnext[j]; vnext[j] = buf[cn * P + j]; }
                 unsigned bits = 0u;
 #pragma unroll
                 for (int j = E - 1; j >= 0; --j) {
                     const int x = lane * E + j;
-                    const float val = buf[c * P + x];
+                    const float val = vcur[j];
                     const float above = (j == 0) ? up : V[j - 1];               // V[x-1, y-1]
                     const float v_prev = (x == 0) ? (y == 0 ? 0.f : neg) : above;   // core.pyx:23-29
                     const float v_cur = (x == y) ? neg : V[j];                  // core.pyx:19-22

@@ -43,6 +43,39 @@ class RowMap:
         self._keep = dev
 
 
+class DeviceRowMap:
+    """The same packed row axis with a FIXED geometry -- every utterance owns `sq_max` rows plus guards -- and the
+    validity of each row decided on the device from device-resident lengths (`update`).  No host copy of the
+    lengths is needed, so a decoder call that uses it is sync-free and CUDA-graph capturable (GlowTTS.inference
+    predicts the mel lengths on the device, Modules.py:173-174).  Padding rows are computed and masked."""
+
+    def __init__(self, batch, sq_max, device):
+        self.batch, self.sq_max = int(batch), int(sq_max)
+        self.stride = self.sq_max + GUARD
+        pos = GUARD + self.batch * self.stride
+        self.rows_pad = max(ROW_TILE, (pos + ROW_TILE - 1) // ROW_TILE * ROW_TILE)
+        self.rows_real = self.batch * self.sq_max
+        dev = torch.device(device)
+        r = torch.arange(self.rows_pad, device=dev, dtype=torch.int64) - GUARD
+        self._b = torch.div(r, self.stride, rounding_mode="floor")
+        self._t = r - self._b * self.stride
+        self._in = (r >= 0) & (self._b < self.batch) & (self._t < self.sq_max)
+        self._bc = self._b.clamp(0, self.batch - 1)
+        self.row_utt = torch.full((self.rows_pad,), -1, dtype=torch.int32, device=dev)
+        self.row_t = torch.zeros(self.rows_pad, dtype=torch.int32, device=dev)
+        self.utt_off = (GUARD + torch.arange(self.batch, device=dev) * self.stride).to(torch.int32)
+        self.utt_len = torch.zeros(self.batch, dtype=torch.int32, device=dev)
+
+    def update(self, sq_lengths):
+        """sq_lengths: device integer tensor [batch] (clamped to sq_max); stream-ordered, no sync."""
+        n = sq_lengths.to(torch.int64).clamp(0, self.sq_max)
+        valid = self._in & (self._t < n[self._bc])
+        self.row_utt.copy_(torch.where(valid, self._b, torch.full_like(self._b, -1)))
+        self.row_t.copy_(torch.where(valid, self._t, torch.zeros_like(self._t)))
+        self.utt_len.copy_(n)
+        return self
+
+
 _ROWMAP_CACHE = {}
 
 

@@ -215,6 +215,8 @@ class Decoder(torch.nn.Module):
         self._step = 0
         self.host_lengths = None       # optional: set by the caller to skip the D2H sync
         self._prepared = None          # (wpack, wpack_tc) being prepared on the side stream (begin_prepare)
+        self.device_lengths = None     # set around a call by GlowTTS.inference_device: mel lengths as a device tensor
+        self._dev_maps = {}
         self.defer_param_grads = False  # set by train.TrainStep, which joins the side stream before the optimizer
 
     # ---- flat parameter plumbing (see flat.py) ------------------------------------
@@ -299,6 +301,14 @@ class Decoder(torch.nn.Module):
             an.bias.data.copy_((-mean * torch.exp(-half_log_var)).view_as(an.bias))
             an.initialized = True
 
+    def _device_row_map(self, batch, sq_max, device):
+        key = (batch, sq_max, str(device))
+        if key not in self._dev_maps:
+            if len(self._dev_maps) > 16:
+                self._dev_maps.clear()
+            self._dev_maps[key] = _flow.DeviceRowMap(batch, sq_max, device)
+        return self._dev_maps[key]
+
     # ---- forward -----------------------------------------------------------------------
     def forward(self, x, mask, speakers=None, prosodies=None, pitches=None, reverse=False):
         _lib.require_cuda(x, "Decoder input")
@@ -308,13 +318,22 @@ class Decoder(torch.nn.Module):
             raise ValueError("speaker embeddings must be given exactly in SE mode")
         b, c, t = x.shape
         t2 = (t // 2) * 2
-        lens = self.host_lengths if self.host_lengths is not None else _host_lengths(mask=mask)
-        sq_len = [min(n, t2) // 2 for n in lens]
-        # reference: squeezed mask = mask[:, :, 1::2] (Modules.py:903): frame pair kept iff its odd frame is valid
-        rm = _flow.row_map(sq_len, x.device)
         xin = x[:, :, :t2]
-        out_mask = (torch.arange(t2, device=x.device)[None, None, :] <
-                    (2 * _lib.device_ints(sq_len, torch.int64, x.device))[:, None, None]).to(x.dtype)
+        if self.device_lengths is not None:
+            # lengths known on the device only (sync-free inference): fixed-geometry row map, validity per row
+            # decided on the device
+            if not reverse:
+                raise _lib.GlowCoreError("device_lengths is for the reverse (inference) direction")
+            sq_dev = torch.clamp(self.device_lengths.to(torch.int64), max=t2) // 2
+            rm = self._device_row_map(b, t2 // 2, x.device).update(sq_dev)
+            out_mask = (torch.arange(t2, device=x.device)[None, None, :] < (2 * sq_dev)[:, None, None]).to(x.dtype)
+        else:
+            lens = self.host_lengths if self.host_lengths is not None else _host_lengths(mask=mask)
+            sq_len = [min(n, t2) // 2 for n in lens]
+            # reference: squeezed mask = mask[:, :, 1::2] (Modules.py:903): frame pair kept iff its odd frame is valid
+            rm = _flow.row_map(sq_len, x.device)
+            out_mask = (torch.arange(t2, device=x.device)[None, None, :] <
+                        (2 * _lib.device_ints(sq_len, torch.int64, x.device))[:, None, None]).to(x.dtype)
         self.flat_params()
         if reverse:
             with torch.no_grad():
@@ -716,8 +735,48 @@ class GlowTTS(torch.nn.Module):
                 + (-0.5 * mean ** 2 * r).sum(dim=1).unsqueeze(-1))
 
     @torch.no_grad()
+    def inference_device(self, tokens, token_lengths, speakers=None, noise_scale=1.0, length_scale=1.0,
+                         max_mel_length=1000, noises=None):
+        """`inference` without a single host round trip: the reference reads the predicted
+        mel lengths back to size its tensors (Modules.py:174-176); here every tensor has the static length
+        `max_mel_length` (longer predictions are cut there), the lengths stay on the device and the decoder runs
+        on a fixed-geometry row map, so the whole call is one stream of launches -- capturable in a CUDA graph
+        (infer.GraphedInference).  Same arithmetic as `inference`; returns (mels [B,80,max_mel_length],
+        mel_Lengths [B] int64 (device), attentions [B,T_x,max_mel_length])."""
+        d = self.layer_Dict
+        dev = tokens.device
+        _lib.require_cuda(tokens, "tokens")
+        t_mel = int(max_mel_length) // self.num_squeeze * self.num_squeeze
+        spk = d["LUT"](speakers) if "LUT" in d else None
+        t_len = token_lengths.to(device=dev, dtype=torch.int32)
+        token_masks = (torch.arange(tokens.shape[1], device=dev)[None, :] < t_len[:, None]).unsqueeze(1).float()
+        mean, log_std, log_dur, mask = d["Encoder"](tokens, token_masks, spk, None, lengths=t_len)
+        if not torch.is_tensor(length_scale):
+            length_scale = torch.tensor([float(length_scale)], device=dev)
+        length_scale = length_scale.to(dev).unsqueeze(-1).unsqueeze(-1)
+        durations = torch.ceil(torch.exp(log_dur) * mask * length_scale).squeeze(1)          # :173
+        mel_lengths = torch.clamp(durations.sum(dim=1), 1.0, float(t_mel)).long()             # :174, cut at the static size
+        mel_masks = (torch.arange(t_mel, device=dev)[None, :] < mel_lengths[:, None]).unsqueeze(1).float()
+        attention_masks = (token_masks.unsqueeze(-1) * mel_masks.unsqueeze(2)).squeeze(1)
+        attentions = self.Path_Generate(durations, attention_masks)
+        mel_mean = mean @ attentions
+        mel_log_std = log_std @ attentions
+        if noises is None:
+            noises = torch.randn_like(mel_mean)
+        z = (mel_mean + torch.exp(mel_log_std) * (noises[:, :, :t_mel] * noise_scale)) * mel_masks
+        dec = d["Decoder"]
+        dec.device_lengths = mel_lengths
+        try:
+            mels, _, mel_masks = dec(z, mel_masks, spk, None, None, reverse=True)
+        finally:
+            dec.device_lengths = None
+        mels = mels.masked_fill(mel_masks == 0.0, -self.max_abs_mel)
+        return mels, mel_lengths, attentions
+
+    @torch.no_grad()
     def inference(self, tokens, token_lengths, mels_for_prosody=None, mel_lengths_for_prosody=None, speakers=None,
-                  mels_for_ge2e=None, pitches=None, pitch_lengths=None, noise_scale=1.0, length_scale=1.0):
+                  mels_for_ge2e=None, pitches=None, pitch_lengths=None, noise_scale=1.0, length_scale=1.0,
+                  noises=None):
         d = self.layer_Dict
         dev = tokens.device
         _lib.require_cuda(tokens, "tokens")
@@ -737,7 +796,9 @@ class GlowTTS(torch.nn.Module):
         attentions = self.Path_Generate(durations, attention_masks)
         mel_mean = mean @ attentions
         mel_log_std = log_std @ attentions
-        noises = torch.randn_like(mel_mean) * noise_scale
+        if noises is None:
+            noises = torch.randn_like(mel_mean)
+        noises = noises[:, :, :mel_mean.shape[2]] * noise_scale
         z = (mel_mean + torch.exp(mel_log_std) * noises) * mel_masks                          # :191
         mels, _, mel_masks = d["Decoder"](z, mel_masks, spk, None, None, reverse=True)
         mels = mels.masked_fill(mel_masks == 0.0, -self.max_abs_mel)                           # :202

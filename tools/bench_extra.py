@@ -131,7 +131,8 @@ def run_mas(args, bench):
                          "paths_equal_gpu": same},
         "grid": grid,
     }
-    print(json.dumps(line), flush=True)
+    import bench
+    bench.emit_json(line)
     return 0
 
 
@@ -191,7 +192,67 @@ def run_decoder(args, bench):
                                  "frac": gbs / pk["hbm_gbs"], "note": "algorithmic 1920*s B per mel frame (SURVEY 8d)"},
         "sweep": sweep,
     }
-    print(json.dumps(line), flush=True)
+    import bench
+    bench.emit_json(line)
+    return 0
+
+
+def run_inference(args, bench):
+    """GlowTTS.inference end to end (text -> mel): the CUDA-graph serving path (infer.GraphedInference) against
+    the eager call with its host round trips.  Request = B sentences of ~100 tokens from pinned host memory;
+    the timed region has the H2D copy of the tokens, the replay and the D2H read of the mel lengths."""
+    import torch
+    from glow_tts_b200.infer import GraphedInference
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    model, hp = bench.build_cpu_model("Vanilla", args.precision)
+    for blk in model.layer_Dict["Decoder"].layer_Dict["Flows"]:
+        blk.layers[0].initialized = True
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    rows = []
+    for b in (1, 16):
+        t_text, t_mel = 128, 1000
+        lens = torch.randint(60, 121, (b,), generator=g)
+        tokens = torch.randint(2, 35, (b, t_text), generator=g)
+        tokens[:, 0] = 0
+        for i in range(b):
+            tokens[i, int(lens[i]) - 1:] = 1
+        tokens, lens = tokens.pin_memory(), lens.to(torch.int32).pin_memory()
+        # the duration predictor of a random-init model predicts ~1 frame per token; stretch to a speech-like 6
+        gi = GraphedInference(model, b, t_text, t_mel, noise_scale=0.667, length_scale=6.0, warmup=3)
+        iters = max(args.steps, 10)
+        for _ in range(3):
+            gi.run(tokens, lens)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            mels, ml = gi.run(tokens, lens)
+            frames = int(ml.sum().item())                       # the D2H read a server needs to cut the mels
+        ms_graph = (time.perf_counter() - t0) / iters * 1e3
+        for _ in range(3):
+            model.inference(tokens=tokens.to(dev), token_lengths=lens, noise_scale=0.667, length_scale=6.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            m2, ml2, _ = model.inference(tokens=tokens.to(dev, non_blocking=True), token_lengths=lens, noise_scale=0.667,
+                                         length_scale=6.0)
+            frames2 = int(ml2.sum().item())
+        ms_eager = (time.perf_counter() - t0) / iters * 1e3
+        rows.append({"batch": b, "t_text_max": t_text, "t_mel_max": t_mel, "mel_frames": frames,
+                     "ms_graph": ms_graph, "ms_eager": ms_eager, "launches_per_replay": gi.launches_per_replay,
+                     "mel_frames_per_s_graph": frames / (ms_graph * 1e-3), "mel_frames_per_s_eager": frames2 / (ms_eager * 1e-3)})
+    top = rows[-1]
+    line = {
+        "metric": "inference_mel_frames_per_sec", "value": top["mel_frames_per_s_graph"], "unit": "mel-frames/s",
+        "n_gpus": 1, "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": top["ms_graph"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "GlowTTS.inference text->mel, B=16 sentences of 60-120 tokens, static T_mel=1000, "
+                               "CUDA-graph replay (infer.GraphedInference); host-timed incl. H2D tokens + D2H lengths",
+                   "l2": "not flushed: a serving request is latency-bound, ~60 MB of activations per call"},
+        "latency_ms_batch1": rows[0]["ms_graph"], "rows": rows,
+    }
+    bench.emit_json(line)
     return 0
 
 
@@ -201,4 +262,6 @@ def run(args):
         return 0
     if args.workload == "mas":
         return run_mas(args, bench)
+    if args.workload == "inference":
+        return run_inference(args, bench)
     return run_decoder(args, bench)

@@ -196,6 +196,7 @@ class GraphedTrainStep:
         self.mels = torch.empty(mels.shape, dtype=mels.dtype, device=dev)
         self.spk = torch.empty(spk.shape, dtype=spk.dtype, device=dev)
         self.gf, self.gp = global_frames, global_positions
+        self._copy_stream = self._staging = self._staged = None
         step.opt.use_device_schedule()
         self.load(batch_host)
         cur = torch.cuda.current_stream(dev)
@@ -233,12 +234,41 @@ class GraphedTrainStep:
         self.mels.copy_(mels, non_blocking=True)
         self.spk.copy_(spk, non_blocking=True)
 
+    def prefetch(self, batch_host):
+        """Start the H2D copy of a LATER step's batch now, on a copy stream, into staging buffers: it overlaps the
+        step in flight (what a data loader's pinned, non_blocking prefetch does).  `run(batch_host)` with the same
+        object then only moves staging -> static buffers on the device."""
+        if self._key(batch_host[1], batch_host[3]) != self.key:
+            self._staged = None
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._staging = tuple(torch.empty_like(t) for t in (self.tokens, self.mels, self.spk))
+            self._staged_ready = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream(self.device))
+        tokens, _, mels, _, spk = batch_host
+        self._copy_stream.wait_event(self._staging_free)       # the previous staging -> static move has finished
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._staging, (tokens, mels, spk)):
+                dst.copy_(src, non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._staged = batch_host
+
     def run(self, batch_host=None):
         """One optimizer step.  batch_host=None re-uses the resident inputs."""
         if batch_host is not None:
             if self._key(batch_host[1], batch_host[3]) != self.key:
                 return self.step.run(self.step.to_device(batch_host), self.gf, self.gp)
-            self.load(batch_host)
+            if self._staged is batch_host:                      # prefetched: device-to-device, already resident
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(self._staged_ready)
+                for dst, src in zip((self.tokens, self.mels, self.spk), self._staging):
+                    dst.copy_(src, non_blocking=True)
+                self._staging_free.record(cur)
+                self._staged = None
+            else:
+                self.load(batch_host)
         opt = self.step.opt
         opt.upload(opt.advance(1.0 / self.step.world))
         self.graph.replay()

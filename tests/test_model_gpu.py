@@ -117,6 +117,36 @@ def test_graphed_train_steps_match_reference(case):
     assert abs(float(flat.double().norm()) - g["train_param_digest"][0]) < 1e-4 * g["train_param_digest"][0]
 
 
+def test_prefetched_batches_reach_the_graph():
+    """GraphedTrainStep.prefetch stages a later step's batch on a copy stream; run() with the same object must
+    train on exactly that data: same losses as the plain load() path, and different data gives different losses."""
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep, GraphedTrainStep
+    from tests._util import synth_batch
+    mode, tls, mls, bseed, wseed = CASES["vanilla_small"]
+    other = synth_batch(bseed + 7, tls, mls)                   # same geometry, different tokens and mels
+    runs = {}
+    for how in ("load", "prefetch"):
+        model, sd, g, batch, _ = load_case("vanilla_small", "fp32")
+        model.eval()
+        step = TrainStep(model, load_hparams(Mode=mode, Precision="fp32"), torch.device("cuda:0"))
+        graphed = GraphedTrainStep(step, batch, warmup=1)
+        pinned = [tuple(t.pin_memory() if torch.is_tensor(t) and not t.is_cuda else t for t in b) for b in (other, batch)]
+        losses = []
+        if how == "prefetch":
+            graphed.prefetch(pinned[0])
+        for i in range(4):
+            cur = pinned[i % 2]
+            graphed.run(cur)
+            if how == "prefetch":
+                graphed.prefetch(pinned[(i + 1) % 2])
+            losses.append(float(graphed.last["mle"]))
+        runs[how] = losses
+    for a, b in zip(runs["load"], runs["prefetch"]):
+        assert abs(a - b) < 1e-5 * abs(a), runs          # same data path up to atomic-order rounding
+    assert abs(runs["load"][0] - runs["load"][1]) > 1e-4, runs
+
+
 def test_graph_replays_draw_fresh_dropout_masks():
     """Two replays of one captured training step must not reuse the dropout masks: the kernels mix the
     device step counter into their seeds (glow_flow_call.step_dev / glow_attn_call.step_dev)."""

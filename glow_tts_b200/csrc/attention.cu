@@ -431,12 +431,26 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi)
 // rows [t0, t0 + n) of one head of a packed-row tensor -> bf16 tile rows (zeros beyond the sentence)
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16 *tile, const float *base, int ld, int t0, int n, int len, int tid)
 {
-    for (int e = tid; e < n * (kAD / 4); e += kMThreads) {
-        const int r = e / (kAD / 4), c4 = e - r * (kAD / 4);
-        const int t = t0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < len) v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)t * ld) + c4);
-        *reinterpret_cast<uint2 *>(tile + (size_t)r * kMP + c4 * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    // 8 loads in flight per thread: with one load per iteration the 4 warps of a CTA spend ~40 dependent
+    // L2 round trips on a 208-row K or V tile, which was most of the kernel's time
+    constexpr int U = 8;
+    const int total = n * (kAD / 4);
+    for (int e0 = tid; e0 < total; e0 += kMThreads * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kMThreads;
+            const int r = e / (kAD / 4), c4 = e - r * (kAD / 4);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < total && t0 + r < len) v[u] = __ldg(reinterpret_cast<const float4 *>(base + (size_t)(t0 + r) * ld) + c4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kMThreads;
+            const int r = e / (kAD / 4), c4 = e - r * (kAD / 4);
+            if (e < total)
+                *reinterpret_cast<uint2 *>(tile + (size_t)r * kMP + c4 * 4) = make_uint2(pack2(v[u].x, v[u].y), pack2(v[u].z, v[u].w));
+        }
     }
 }
 
@@ -767,18 +781,37 @@ rpr_attn_bwd_kv_mma_kernel(const AttnArgs a)
     const float inv_keep = 1.f / (1.f - a.drop_p);
     load_rows_bf16(Qs, a.q + off, a.ld, 0, TQ, len, tid);
     load_rows_bf16(Ds, a.dout + off, a.ld, 0, TQ, len, tid);
-    for (int e = tid; e < TQ * kMQ; e += kMThreads) {
-        const int i = e >> 6, jj = e & 63;
-        const int j = j0 + jj;
-        float pd = 0.f, ds = 0.f;
-        if (i < len && j < len) {
-            const size_t idx = ((size_t)(b * a.H + h) * T + i) * T + j;
-            pd = a.probs[idx];
-            if (seed != 0) pd = attn_keep(seed, idx, a.drop_p) ? pd * inv_keep : 0.f;
-            ds = a.ds[idx];
+    {   // 8 (probability, dS) pairs in flight per thread (one pair per iteration was ~100 dependent round trips)
+        constexpr int U = 8;
+        const int total = TQ * kMQ;
+        for (int e0 = tid; e0 < total; e0 += kMThreads * U) {
+            float pd[U], ds[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * kMThreads;
+                const int i = e >> 6, j = j0 + (e & 63);
+                pd[u] = 0.f;
+                ds[u] = 0.f;
+                if (e < total && i < len && j < len) {
+                    const size_t idx = ((size_t)(b * a.H + h) * T + i) * T + j;
+                    pd[u] = __ldg(a.probs + idx);
+                    ds[u] = __ldg(a.ds + idx);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * kMThreads;
+                if (e >= total) continue;
+                const int i = e >> 6, jj = e & 63;
+                float p = pd[u];
+                if (seed != 0 && i < len && j0 + jj < len) {
+                    const size_t idx = ((size_t)(b * a.H + h) * T + i) * T + j0 + jj;
+                    p = attn_keep(seed, idx, a.drop_p) ? p * inv_keep : 0.f;
+                }
+                Pt[i * kMKP + jj] = p;
+                St[i * kMKP + jj] = ds[u];
+            }
         }
-        Pt[i * kMKP + jj] = pd;
-        St[i * kMKP + jj] = ds;
     }
     __syncthreads();
     const int m0 = warp * 16, g = lane >> 2, t2 = (lane & 3) * 2;

@@ -255,6 +255,23 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
                                                                                    c.rows.row_utt, R, DOUTS, DY);
         GLOW_CHECK_LAUNCH("coupling_bwd_kernel");
         GLOW_TRY(Ops::b_end(c, k, DOUTS, DOUT));
+        // Weight gradients go to the side stream AS SOON AS their operands exist (one fork per producer below),
+        // not after the whole block: the last block's 13 GEMMs would otherwise all trail the data-gradient chain.
+        const int wm = kBf16 ? 1 : 0;
+        auto fork = [&]() -> int {
+            GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
+            return GLOW_OK;
+        };
+        GLOW_TRY(fork());                                  // DOUTS, DOUT are final
+        // dW_end[192][160] = OUT^T DOUTS
+        GLOW_TRY(wgrad_gemm(side, wm, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f, true, true));
+        // dW_rs[192][rs_n], skip columns (d(out)); the last layer has only those
+        for (int i = kLayers - 1; i >= 0; --i) {
+            const bool last = i == kLayers - 1;
+            GLOW_TRY(wgrad_gemm(side, wm, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + (last ? 0 : kH), last ? kH : kG,
+                                1, 0, 0, 0.f, true, true));
+        }
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
             const ActT *DHnext = last ? nullptr : DH[i + 1];
@@ -270,32 +287,19 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
                 GLOW_CHECK_LAUNCH("spk_bwd_kernel");
             }
             GLOW_TRY(Ops::b_in(c, k, i, DPRE[i], DHnext, DH[i]));
+            GLOW_TRY(fork());                              // DPRE[i], DH[i] are final
+            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
+            GLOW_TRY(wgrad_gemm(side, wm, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
+                                kTaps, kH, (long long)kH * kG, 0.f, true, true));
+            if (i > 0) {        // res columns of the layer below from d(h_i)
+                GLOW_TRY(wgrad_gemm(side, wm, b.ACTS[i - 1], kH, DH[i], kH, R, kH, kH, dwp + c.bp.rs_w[i - 1], kG, 1, 0, 0, 0.f, true, true));
+            } else if (kBf16) {
+                GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
+            } else {
+                GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
+            }
         }
         GLOW_TRY(Ops::b_start(c, k, DH[0], DY));
-        // ---- weight / bias gradients of this block (side stream)
-        GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
-        GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
-        // dW_end[192][160] = OUT^T DOUTS
-        GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f, true, true));
-        for (int i = kLayers - 1; i >= 0; --i) {
-            const bool last = i == kLayers - 1;
-            const int rs_n = last ? kH : kG;
-            // dW_rs[192][rs_n]: res columns from d(h_{i+1}), skip columns from d(out)
-            if (!last) {
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DH[i + 1], kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true, true));
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + kH, rs_n, 1, 0, 0, 0.f, true, true));
-            } else {
-                GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i], rs_n, 1, 0, 0, 0.f, true, true));
-            }
-            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
-            GLOW_TRY(wgrad_gemm(side, kBf16 ? 1 : 0, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
-                                kTaps, kH, (long long)kH * kG, 0.f, true, true));
-        }
-        if (kBf16) {
-            GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
-        } else {
-            GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
-        }
         GLOW_TRY(wgrad_flush(side));                       // the block's split reductions, one launch
         {   // every bias gradient of the block: column sums of the gradients the GEMMs above read (one launch)
             ColsumJobs<ActT> cj{};

@@ -79,6 +79,7 @@ SIGNATURES = {
     "glow_flow_forward": (_I, [_PCALL, _P, _P, _P]),
     "glow_flow_reverse": (_I, [_PCALL, _P, _P, _F]),
     "glow_flow_backward": (_I, [_PCALL, _P, _P, _P, _P, _P]),
+    "glow_flow_backward_params": (_I, [_PCALL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_flow_param_grads": (_I, [_PCFG, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "glow_rpr_attention_forward": (_I, [_PATTN, _P, _P, _P]),
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),

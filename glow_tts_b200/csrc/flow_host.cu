@@ -75,15 +75,16 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
 // Build the per-tensor job table from the flat parameter buffer + host offset table.
 static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *off, float *grads,
                        float *wpack, __nv_bfloat16 *wpack_tc, const float *dwpack, WnJobs *jobs, SmallJobs *small,
-                       bool tc_only = false)
+                       bool tc_only = false, int k0 = 0, int k1 = -1)
 {
+    if (k1 < 0) k1 = cfg.blocks;
     const bool se = cfg.spk_dim > 0;
     const int per_block = slots_per_block(se);
     const BlockPack bp = make_block_pack(cfg.spk_dim);
     const BlockPackTC bt = make_block_pack_tc();
     jobs->count = 0;
     int cta = 0;
-    small->blocks = cfg.blocks;
+    small->blocks = k1 - k0;
     auto slice_of = [](int n) { return n == kG ? kBnGate : n == kH ? kBnH : n == kC ? kBnEnd : kBnHalf; };
     auto add = [&](const int64_t *o, int sb, int sg, int sv, int n_out, int k_in, int taps, int il, float *wp,
                    const float *dwp, size_t W, size_t WT, size_t B, __nv_bfloat16 *tp, size_t sW, size_t sWT,
@@ -109,17 +110,17 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
         j.skip_f32 = (tc_only && has_tc) ? 1 : 0;
         cta += n_out / 8;
     };
-    for (int k = 0; k < cfg.blocks; ++k) {
+    for (int k = k0; k < k1; ++k) {
         const int64_t *o = off + (size_t)k * per_block;
         float *wp = wpack ? wpack + (size_t)k * bp.total : nullptr;
         const float *dwp = dwpack ? dwpack + (size_t)k * bp.total : nullptr;
         __nv_bfloat16 *tp = wpack_tc ? wpack_tc + (size_t)k * bt.total : nullptr;
-        small->logs[k] = params + o[P_AN_LOGS];
-        small->bias[k] = params + o[P_AN_BIAS];
-        small->w[k] = params + o[P_INV_W];
-        small->dlogs[k] = grads ? grads + o[P_AN_LOGS] : nullptr;
-        small->dbias[k] = grads ? grads + o[P_AN_BIAS] : nullptr;
-        small->dw[k] = grads ? grads + o[P_INV_W] : nullptr;
+        small->logs[k - k0] = params + o[P_AN_LOGS];
+        small->bias[k - k0] = params + o[P_AN_BIAS];
+        small->w[k - k0] = params + o[P_INV_W];
+        small->dlogs[k - k0] = grads ? grads + o[P_AN_LOGS] : nullptr;
+        small->dbias[k - k0] = grads ? grads + o[P_AN_BIAS] : nullptr;
+        small->dw[k - k0] = grads ? grads + o[P_INV_W] : nullptr;
         add(o, P_START_B, P_START_G, P_START_V, kH, kCh, 1, 0, wp, dwp, bp.start_w, bp.start_wt, bp.start_b, tp,
             bt.start_w, bt.start_wt, true);
         for (int i = 0; i < kLayers; ++i) {
@@ -137,6 +138,23 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
         add(o, e + 1, -1, e, kC, kH, 1, 1, wp, dwp, bp.end_w, bp.end_wt, bp.end_b, tp, bt.end_w, bt.end_wt, true);
     }
     jobs->total_ctas = cta;
+}
+
+int param_grads_block(const FlowCfg &cfg, const float *params, const int64_t *offsets_host, const float *wpack,
+                      const float *dwpack, const float *dlogdet, const int32_t *utt_len, int batch, float *grads, int block,
+                      cudaStream_t st)
+{
+    static thread_local WnJobs jobs;
+    SmallJobs small{};
+    build_jobs(cfg, params, offsets_host, grads, const_cast<float *>(wpack), nullptr, dwpack, &jobs, &small, false, block,
+               block + 1);
+    small.batch = batch;
+    const BlockPack bp = make_block_pack(cfg.spk_dim);
+    // small_grad_kernel indexes blocks from its base pointers: hand it this block's slices
+    int rc = launch_small_grad(small, wpack + (size_t)block * bp.total, dwpack + (size_t)block * bp.total, bp.total, bp,
+                               dlogdet, utt_len, st);
+    if (rc) return rc;
+    return launch_wn_grad(jobs, st);
 }
 
 }  // namespace glow
@@ -244,6 +262,27 @@ int glow_flow_backward(const glow_flow_call *call, const float *dz, const float 
         return flow_backward_f32(make_ctx<float>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk);
     return flow_backward_bf16(make_ctx<__nv_bfloat16>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk,
                               call->precision == GLOW_BF16);
+}
+
+int glow_flow_backward_params(const glow_flow_call *call, const float *dz, const float *dlogdet, float *dwpack,
+                              float *dmel, float *dspk, const float *params, const int64_t *offsets_host, float *grads)
+{
+    int rc = check_call(call, true);
+    if (rc) return rc;
+    GLOW_REQUIRE(dz && dlogdet && dwpack && params && offsets_host && grads, GLOW_ERR_INVALID,
+                 "flow_backward_params: null pointer");
+    GLOW_REQUIRE(!(call->cfg.spk_dim > 0) || dspk, GLOW_ERR_INVALID, "flow_backward_params: SE needs dspk");
+    if (dspk)
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dspk, 0, sizeof(float) * call->batch * call->cfg.spk_dim,
+                                        (cudaStream_t)call->stream));
+    if (call->precision == GLOW_F32) {
+        FlowCtx<float> c = make_ctx<float>(call);
+        c.pg_params = params; c.pg_offsets = offsets_host; c.pg_grads = grads;
+        return flow_backward_f32(c, dz, call->t_max, dlogdet, dwpack, dmel, dspk);
+    }
+    FlowCtx<__nv_bfloat16> c = make_ctx<__nv_bfloat16>(call);
+    c.pg_params = params; c.pg_offsets = offsets_host; c.pg_grads = grads;
+    return flow_backward_bf16(c, dz, call->t_max, dlogdet, dwpack, dmel, dspk, call->precision == GLOW_BF16);
 }
 
 }  // extern "C"

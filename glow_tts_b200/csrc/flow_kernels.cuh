@@ -65,7 +65,17 @@ struct FlowCtx {
     const uint64_t *step_dev;        // optional device step counter mixed into seed
     bool training;                   // keep per-block activations
     cudaStream_t st;
+    // glow_flow_backward_params: convert every block's effective-weight gradients to parameter gradients on the
+    // side stream as soon as the block is done (null: the caller runs glow_flow_param_grads afterwards)
+    const float *pg_params = nullptr;
+    const int64_t *pg_offsets = nullptr;
+    float *pg_grads = nullptr;
 };
+
+// weight_norm / ActNorm / 4x4 backward of ONE block (flow_host.cu): dwpack -> flat parameter gradients
+int param_grads_block(const FlowCfg &cfg, const float *params, const int64_t *offsets_host, const float *wpack,
+                      const float *dwpack, const float *dlogdet, const int32_t *utt_len, int batch, float *grads, int block,
+                      cudaStream_t st);
 
 // forward / reverse / backward over all blocks, fp32 CUDA-core path (flow_simt.cu)
 int flow_forward_f32(const FlowCtx<float> &c, const float *mel, int T, float *z, float *logdet);
@@ -84,7 +94,9 @@ int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, 
 struct SideStream {
     cudaStream_t stream;
     cudaStream_t enc_stream;             // the encoder's weight gradients: its backward overlaps the decoder's
+    cudaStream_t aux;                    // bias-gradient column sums of a decoder block, next to its weight-gradient GEMMs
     cudaEvent_t fork[2], done[2];        // decoder backward, per block parity
+    cudaEvent_t aux_fork, aux_done[2];
     cudaEvent_t enc_fork, enc_done;      // encoder weight gradients (rows_conv.cu)
     bool enc_pending;                    // enc_done has been recorded since the last glow_side_join
 };

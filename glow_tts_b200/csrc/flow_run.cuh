@@ -243,7 +243,10 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
     const int Rw = R - 2 * G2;
     for (int k = c.cfg.blocks - 1; k >= 0; --k) {
         const int set = k & 1;
-        if (k + 2 < c.cfg.blocks) GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[set], 0));   // set is free again
+        if (k + 2 < c.cfg.blocks) {                                                                // set is free again
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[set], 0));
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->aux_done[set], 0));
+        }
         Bufs<ActT> b = block_bufs(c, k);
         float *dwp = dwpack + (size_t)k * c.bp.total;
         ActT *DOUTS = c.bw_act + c.wl.douts[set], *DOUT = c.bw_act + c.wl.dout[set];
@@ -300,7 +303,6 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             }
         }
         GLOW_TRY(Ops::b_start(c, k, DH[0], DY));
-        GLOW_TRY(wgrad_flush(side));                       // the block's split reductions, one launch
         {   // every bias gradient of the block: column sums of the gradients the GEMMs above read (one launch)
             ColsumJobs<ActT> cj{};
             auto add = [&](const ActT *src, int n, float *d0, float *d1 = nullptr, float *d2 = nullptr, float *d3 = nullptr) {
@@ -313,19 +315,34 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             for (int i = 0; i < kLayers - 1; ++i) add(DH[i + 1], kH, dwp + c.bp.rs_b[i]);
             for (int i = 0; i < kLayers; ++i) add(DPRE[i], kG, dwp + c.bp.in_b[i]);
             add(DH[0], kH, dwp + c.bp.start_b);
-            colsum_multi_kernel<ActT><<<dim3(R / 128, cj.count), 192, 0, side>>>(cj, R);
+            // on a third stream, next to the GEMMs (its sources are final since the last fork)
+            GLOW_CHECK_CUDA(cudaEventRecord(ss->aux_fork, c.st));
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(ss->aux, ss->aux_fork, 0));
+            colsum_multi_kernel<ActT><<<dim3(R / 128, cj.count), 192, 0, ss->aux>>>(cj, R);
             GLOW_CHECK_LAUNCH("colsum_multi_kernel");
+            GLOW_CHECK_CUDA(cudaEventRecord(ss->aux_done[set], ss->aux));
         }
-        GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
+        GLOW_TRY(wgrad_flush(side));                       // the block's split reductions, one launch
         // ---- back on the main stream: 4x4 mix + ActNorm backward -> dz of the previous block
         const bool need_dz = k > 0 || dmel != nullptr;
         mix_bwd_kernel<<<R / kMixRows, 256, 0, c.st>>>(DY, b.Y, c.rows.row_utt, R, c.wpack + (size_t)k * c.bp.total, c.bp, dwp,
                                                 need_dz ? DZ : nullptr);
         GLOW_CHECK_LAUNCH("mix_bwd_kernel");
+        if (c.pg_grads != nullptr) {
+            // this block's effective-weight gradients are complete once the side stream, the bias sums and
+            // mix_bwd (ActNorm / 4x4 gradients) are: convert them to parameter gradients now, on the side stream
+            GLOW_TRY(fork());
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->aux_done[set], 0));
+            GLOW_TRY(param_grads_block(c.cfg, c.pg_params, c.pg_offsets, c.wpack, dwpack, dlogdet, c.rows.utt_len, B,
+                                       c.pg_grads, k, side));
+        }
+        GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
     }
     // join: every forked block must be back before the caller reads dwpack (and before a capture ends)
-    GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[0], 0));
-    if (c.cfg.blocks > 1) GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[1], 0));
+    for (int i = 0; i < (c.cfg.blocks > 1 ? 2 : 1); ++i) {
+        GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->done[i], 0));
+        GLOW_CHECK_CUDA(cudaStreamWaitEvent(c.st, ss->aux_done[i], 0));
+    }
     if (dmel != nullptr) {
         unpack_rows_kernel<<<dim3((T + 63) / 64, B), 256, 0, c.st>>>(DZ, c.rows.utt_off, c.rows.utt_len, T, dmel, 0.f);
         GLOW_CHECK_LAUNCH("unpack_rows_kernel");

@@ -45,6 +45,9 @@ int side_stream(SideStream **out)
         SideStream &s = g_side[dev];
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.enc_stream, cudaStreamNonBlocking));
+        GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+        GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.aux_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.aux_done[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));

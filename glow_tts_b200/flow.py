@@ -3,6 +3,7 @@ preparation and the autograd bridge to libglowcore's glow_flow_* entry points
 (include/glowcore.h).  Mirrors what Modules.py:286-309 (Decoder) drives in the
 reference; no arithmetic happens in Python."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -97,6 +98,11 @@ def row_map(sq_lengths, device):
 # capturable, so the overlap survives in the CUDA graph.)
 _SIDE = {}
 _SIDE_BUSY = set()
+# GLOW_FUSED_PARAM_GRADS=1: glow_flow_backward_params -- every block's parameter gradients inside the backward call,
+# right behind that block's weight gradients.  Off by default: measured 0.1 ms/step SLOWER at B = 32 (the extra
+# memory traffic lands in the middle of the data-gradient chain instead of in the idle tail); default is one
+# glow_flow_param_grads pass after the backward, on the torch side stream.
+FUSED_PARAM_GRADS = os.environ.get("GLOW_FUSED_PARAM_GRADS", "0") == "1"
 
 
 def side_stream(device):
@@ -261,6 +267,14 @@ class FlowDecoderFn(torch.autograd.Function):
         gflat, direct = owner.flat_grads()
         with torch.cuda.device(device):
             call.stream = torch.cuda.current_stream(device).cuda_stream
+            if direct and owner.defer_param_grads and FUSED_PARAM_GRADS:
+                # gradients land in the attached flat buffer: every block's parameter gradients are produced on the
+                # library's side stream right behind that block's weight gradients
+                rc = _lib.lib().glow_flow_backward_params(ctypes.byref(call), _lib.ptr(dz), _lib.ptr(dlogdet),
+                                                          _lib.ptr(dwp), _lib.ptr(dmel), _lib.ptr(dspk), _lib.ptr(flat),
+                                                          offs.ctypes.data, _lib.ptr(gflat))
+                _lib.check(rc, "glow_flow_backward_params")
+                return (None, None, dmel, dspk, None) + (None,) * ctx.n_params
             rc = _lib.lib().glow_flow_backward(ctypes.byref(call), _lib.ptr(dz), _lib.ptr(dlogdet), _lib.ptr(dwp),
                                                _lib.ptr(dmel), _lib.ptr(dspk))
             _lib.check(rc, "glow_flow_backward")

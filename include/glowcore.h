@@ -249,6 +249,17 @@ int    glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel,
  * layout as wpack, overwritten), optional dmel [batch,80,t_max], dspk [batch,spk_dim]. */
 int    glow_flow_backward(const glow_flow_call *call, const float *dz, const float *dlogdet,
                           float *dwpack, float *dmel, float *dspk);
+
+/*
+ * glow_flow_backward and glow_flow_param_grads in one call: each block's
+ * effective-weight gradients are turned into parameter gradients (weight_norm
+ * backward, ActNorm / 4x4 terms; accumulated into `grads`, laid out like
+ * `params`) on the library's side stream as soon as that block's backward is
+ * done, instead of in one pass after the last block.  Same results.
+ */
+int    glow_flow_backward_params(const glow_flow_call *call, const float *dz, const float *dlogdet,
+                                 float *dwpack, float *dmel, float *dspk,
+                                 const float *params, const int64_t *offsets_host, float *grads);
 /* dwpack -> gradients of the reference parameters (through weight_norm, exp, logdet), += into grads. */
 int    glow_flow_param_grads(const glow_flow_config *cfg, const float *params,
                              const int64_t *offsets_host, const float *wpack,

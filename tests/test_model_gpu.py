@@ -147,6 +147,27 @@ def test_prefetched_batches_reach_the_graph():
     assert abs(runs["load"][0] - runs["load"][1]) > 1e-4, runs
 
 
+def test_per_block_parameter_gradients_equal_the_single_pass(monkeypatch):
+    """glow_flow_backward_params (parameter gradients per block inside the backward call) against the default
+    glow_flow_backward + glow_flow_param_grads: same flat gradient buffer after one step's backward."""
+    from glow_tts_b200 import flow
+    from glow_tts_b200.hparams import load_hparams
+    from glow_tts_b200.train import TrainStep
+    grads = {}
+    for fused in (False, True):
+        monkeypatch.setattr(flow, "FUSED_PARAM_GRADS", fused)
+        model, sd, g, batch, mode = load_case("se_small", "fp32")
+        model.eval()
+        step = TrainStep(model, load_hparams(Mode=mode, Precision="fp32"), torch.device("cuda:0"))
+        step.opt.lr0 = 0.0
+        step.run(step.to_device(batch))
+        torch.cuda.synchronize()
+        grads[fused] = step.flat.grad.detach().clone()
+    scale = grads[False].abs().max().item()
+    assert scale > 0
+    assert (grads[True] - grads[False]).abs().max().item() < 1e-5 * scale
+
+
 def test_graph_replays_draw_fresh_dropout_masks():
     """Two replays of one captured training step must not reuse the dropout masks: the kernels mix the
     device step counter into their seeds (glow_flow_call.step_dev / glow_attn_call.step_dev)."""

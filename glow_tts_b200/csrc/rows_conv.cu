@@ -72,14 +72,24 @@ rows_pack_kernel(const float *__restrict__ w, int cout, int cin, int taps, int b
     }
 }
 
-// grad[n][k][tap] += dwt[tap][k][n]   (cuBLAS result -> torch Conv1d layout, accumulated)
+// grad[n][k][tap] += dwt[tap][k][n]   (cuBLAS result -> torch Conv1d layout, accumulated).  One CTA per 32 x 32
+// (k, n) tile and all taps, transposed through shared memory: reads run along n, the read-modify-write along (k, tap).
+constexpr int kAccTaps = 5;
 __global__ void __launch_bounds__(256)
 rows_wgrad_accum_kernel(const float *__restrict__ dwt, float *__restrict__ grad, int cout, int cin, int taps)
 {
-    const int total = cout * cin * taps;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-        const int n = i % cout, k = (i / cout) % cin, tap = i / (cout * cin);     // coalesced read of dwt
-        grad[((size_t)n * cin + k) * taps + tap] += dwt[i];
+    __shared__ float tile[kAccTaps][32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32, tid = threadIdx.x;
+    for (int e = tid; e < taps * 32 * 32; e += 256) {
+        const int nn = e & 31, kk = (e >> 5) & 31, tap = e >> 10;
+        tile[tap][kk][nn] = dwt[((size_t)tap * cin + k0 + kk) * cout + n0 + nn];
+    }
+    __syncthreads();
+    const int span = 32 * taps;                       // (k, tap) run of one output channel inside the tile: contiguous
+    for (int e = tid; e < 32 * span; e += 256) {
+        const int nn = e / span, r = e - nn * span;
+        const int kk = r / taps, tap = r - kk * taps;
+        grad[((size_t)(n0 + nn) * cin + k0) * taps + r] += tile[tap][kk][nn];
     }
 }
 
@@ -259,13 +269,20 @@ int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *c, const flo
     GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, st));
     GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
     const int center = (c->taps - 1) / 2;
-    rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout,
-                    scratch, c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
-    if (rc) return rc;
-    const int total = c->cin * c->cout * c->taps;
-    rows_wgrad_accum_kernel<<<(total + 255) / 256 < 2 * kNumSMs ? (total + 255) / 256 : 2 * kNumSMs, 256, 0, side>>>(
-        scratch, grad_w, c->cout, c->cin, c->taps);
-    GLOW_CHECK_LAUNCH("rows_wgrad_accum_kernel");
+    if (c->taps == 1) {
+        // a 1x1 conv's gradient in torch's [cout][cin][1] layout IS dy^T x: one GEMM that accumulates straight into
+        // the gradient buffer (beta = 1) -- no partials, no reduction, no permute-add (25 of the encoder's 41 convs)
+        rc = wgrad_gemm(side, 2, dy, c->cout, x, c->cin, c->rows_pad, c->cout, c->cin, grad_w, c->cin, 1, 0, 0, 1.f);
+        if (rc) return rc;
+    } else {
+        rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout,
+                        scratch, c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
+        if (rc) return rc;
+        GLOW_REQUIRE(c->taps <= kAccTaps && c->cout % 32 == 0 && c->cin % 32 == 0, GLOW_ERR_UNSUPPORTED,
+                     "rows_conv_backward_weight_accum: shape %d x %d x %d", c->cout, c->cin, c->taps);
+        rows_wgrad_accum_kernel<<<dim3(c->cout / 32, c->cin / 32), 256, 0, side>>>(scratch, grad_w, c->cout, c->cin, c->taps);
+        GLOW_CHECK_LAUNCH("rows_wgrad_accum_kernel");
+    }
     if (grad_b != nullptr) {
         colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, side>>>(dy, c->cout, c->rows_pad, c->cout, grad_b);
         GLOW_CHECK_LAUNCH("colsum_kernel");

@@ -61,3 +61,31 @@ def test_fused_radam_schedule_matches_oracle():
         assert (b1, b2, eps, wd, max_norm, grad_scale) == (0.9, 0.999, 1e-6, 1e-6, 5.0, 0.5)
         ref.epoch += 1
     assert opt.steps == 11 and opt.epoch == 11
+
+
+def test_device_row_map_matches_host_row_map_semantics():
+    """flow.DeviceRowMap (fixed geometry, validity computed from device-resident lengths -- the sync-free inference
+    path) against the invariants of the host-built flow.RowMap: guard rows, per-utterance runs, frame indices."""
+    from glow_tts_b200 import flow
+    batch, sq_max = 5, 37
+    rm = flow.DeviceRowMap(batch, sq_max, "cpu")
+    assert rm.rows_pad % flow.ROW_TILE == 0 and rm.rows_pad >= flow.GUARD + batch * (sq_max + flow.GUARD)
+    for lens in ([37, 0, 12, 1, 30], [5, 5, 5, 5, 5], [99, 37, 36, 0, 0]):          # 99 is clamped to sq_max
+        rm.update(torch.tensor(lens, dtype=torch.int64))
+        want = [min(n, sq_max) for n in lens]
+        assert rm.utt_len.tolist() == want
+        row_utt, row_t = rm.row_utt.numpy(), rm.row_t.numpy()
+        assert int((row_utt >= 0).sum()) == sum(want)
+        assert (row_utt[:flow.GUARD] == -1).all()
+        for b, n in enumerate(want):
+            off = int(rm.utt_off[b])
+            assert (row_utt[off:off + n] == b).all()
+            assert (row_t[off:off + n] == np.arange(n)).all()
+            assert (row_utt[off + n:off + sq_max + flow.GUARD] == -1).all()          # rest of the slot + its guard rows
+            assert (row_utt[off - flow.GUARD:off] == -1).all()
+        # same runs as the host map of the same lengths, only placed on the fixed stride
+        host = flow.RowMap(want, "cpu")
+        assert host.utt_len.tolist() == want
+        for b, n in enumerate(want):
+            ho, do = int(host.utt_off[b]), int(rm.utt_off[b])
+            assert (host.row_t.numpy()[ho:ho + n] == row_t[do:do + n]).all()

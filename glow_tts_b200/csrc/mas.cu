@@ -173,8 +173,10 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
             for (int j = 0; j < E; ++j) vnext[j] = buf[j];
             for (int c = 0; c < cend; ++c) {
                 const int y = (t << 5) + c;
-                const int lo = max(0, tx + y - ty);
-                const int hi = min(tx, y + 1);
+                // No band test (core.pyx:17 only visits max(0, t_x+y-t_y) <= x < min(t_x, y+1)): a cell inside the
+                // band of column y reads (x, y-1) and (x-1, y-1), both inside the band of column y-1 (or replaced by
+                // the sentinel when x == y / x == 0), so whatever the cells outside the band hold is never read by a
+                // cell inside it; they are simply computed too.
                 const float up = __shfl_up_sync(0xffffffffu, V[E - 1], 1);
                 float vcur[E];
                 const int cn = min(c + 1, 31);
@@ -192,7 +194,7 @@ mas_kernel(const float *__restrict__ value, const float *__restrict__ mask,
                     const bool moved = (x != 0) && ((x == y) || (V[j] < above));
                     const float best = (v_prev > v_cur) ? v_prev : v_cur;       // core.pyx:30
                     const float nv = best + val;
-                    V[j] = (x >= lo && x < hi) ? nv : V[j];
+                    V[j] = nv;
                     bits |= (moved ? 1u : 0u) << j;
                 }
                 dir[y * 32 + lane] = (unsigned char)bits;

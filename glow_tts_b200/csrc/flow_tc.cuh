@@ -50,6 +50,7 @@ constexpr int kTcFirstThreads = 384;        // the CTA's FIRST panel is staged b
 constexpr int kTcFirstActive = 360;         // = 24*15 = 20*18 = 10*36
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcMaxStages = 8;
+constexpr int kBInPanel = 96;             // K per A panel of the k = 5 data-gradient GEMM (b_in); 192 = the old two-panel form
 constexpr int kTcSmemCap = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (barriers are static)
 constexpr int kTcStagingFloats = 32 * 33;   // per epilogue warp: 32 rows x 32 columns, pitch 33 (conflict free)
 
@@ -485,10 +486,14 @@ struct TcOps {
     }
     static int b_in(const Ctx &c, int k, int i, const ActT *DPRE, const ActT *DHnext, ActT *DH)
     {
-        TcA a{{DPRE, DPRE + kH, nullptr, nullptr}};
+        // Four A panels of 96 channels instead of two of 192: the two panel buffers shrink from 102 KB to 51 KB and the
+        // weight ring grows from 2 to 3 stages of 36.9 KB.  With 2 stages the MMA loop ran at 154 cycles per MMA
+        // (N = 192 needs 100): 74 KB in flight over a ~1.8 k-cycle bulk-copy round trip is 40 B/clk per SM.
+        constexpr int kKp = kBInPanel;
+        TcA a{{DPRE, DPRE + kKp, DPRE + 2 * kKp, DPRE + 3 * kKp}};
         EpiBwdIn<ActT> e{DHnext, DH, c.rows.row_utt};
-        return gemm_tc3<kH, kBnH, kH, 2, kG, kTaps, -1, kTcKs, 0>(a, ws(c, k) + c.bt.in_wt[i], c.rows.row_utt,
-                                                               c.rows.rows_pad, e, c.st, "b_in");
+        return gemm_tc3<kH, kBnH, kKp, kG / kKp, kG, kTaps, -1, kTcKs, 0>(a, ws(c, k) + c.bt.in_wt[i], c.rows.row_utt,
+                                                                       c.rows.rows_pad, e, c.st, "b_in");
     }
     static int b_start(const Ctx &c, int k, const ActT *DH0, float *DY)
     {

@@ -450,8 +450,20 @@ struct TcOps {
         const bool last = i == kLayers - 1;
         EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
                                drop_cfg(c, k, i)};
-        int rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs, 0>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
+        // GLOW_IN_GATE_PANEL=96: two 96-channel A panels and a 5-stage weight ring instead of one 192-channel panel
+        // and 3 stages (the b_in trade).  Opt-in only: one probe at the end of round 1 showed no gain
+        // (step 6.29 vs 6.31 ms, in_gate 1.04 vs 1.01 ms per step in the bench hook) -- unlike b_in, in_gate's MMA loop
+        // is not paced by the ring -- and it has not been through tests/test_flow_gpu.py with the variable set.
+        static const bool split_panels = [] { const char *e = getenv("GLOW_IN_GATE_PANEL"); return e && atoi(e) == 96; }();
+        int rc;
+        if (split_panels) {
+            TcA a2{{b.H[i], b.H[i] + 96, nullptr, nullptr}};
+            rc = gemm_tc3<kG, kBnGate, 96, 2, kH, kTaps, +1, kTcKs, 0>(a2, ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
+                                                                   c.rows.rows_pad, eg, c.st, "in_gate");
+        } else {
+            rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs, 0>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
                                                                     c.rows.rows_pad, eg, c.st, "in_gate");
+        }
         if (rc) return rc;
         EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
                             c.rows.row_utt, i == 0, last};

@@ -176,7 +176,7 @@ class TrainStep:
 class GraphedTrainStep:
     """One TrainStep.run captured in a CUDA graph and replayed.
 
-    The eager step is CPU-bound (~1600 launches, 14 us of host time each, against ~18 ms of device
+    The eager step is CPU-bound (~1100 launches, ~14 us of host time each = 15 ms, against ~6.5 ms of device
     work at B=32); replaying it as one graph removes the host from the loop.  What makes the capture
     legal and the replays *different steps*:
       * inputs live in static device buffers, refreshed by `load()` (pinned H2D) before a replay;

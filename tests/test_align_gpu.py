@@ -1,6 +1,6 @@
 """GPU tests of the fused kernels around the alignment search (csrc/align.cu): each one
-against the reference's own expression (Modules.py:107-122, 1020-1029) evaluated with torch in fp32 on the same
-device and inputs.  Tolerances: fp32 sums in a different order -> 1e-5 of the largest magnitude; integer outputs exact."""
+against the oracle's restatement of the reference's expression (oracle/glow_oracle.py: log_prior, mle_loss;
+Modules.py:107-122, 1020-1029 -- pure torch, so it is evaluated in fp32 on the same device and inputs).  Tolerances: fp32 sums in a different order -> 1e-5 of the largest magnitude; integer outputs exact."""
 import math
 
 import pytest
@@ -26,10 +26,11 @@ def _inputs(seed=0, c=80):
     return mean * tmask, log_std * tmask, z * mmask, t_len, m_len, tmask, mmask
 
 
-def _ref_log_p(z, mean, log_std):                     # Modules.py:107-116
-    r = torch.exp(-2 * log_std)
-    return ((-0.5 * math.log(2 * math.pi) - log_std).sum(dim=1).unsqueeze(-1) + r.transpose(2, 1) @ (-0.5 * z ** 2)
-            + (mean * r).transpose(2, 1) @ z + (-0.5 * mean ** 2 * r).sum(dim=1).unsqueeze(-1))
+def _ref_log_p(z, mean, log_std):
+    """The oracle's restatement of Modules.py:107-116 (oracle/glow_oracle.py:log_prior, pure torch), evaluated on the
+    device the kernel ran on."""
+    from oracle import glow_oracle
+    return glow_oracle.log_prior(z, mean, log_std)
 
 
 def test_log_p_matches_reference_expression_on_the_valid_corner():
@@ -89,9 +90,10 @@ def test_mle_loss_forward_and_backward_match_the_reference_expression():
     log_dets = torch.randn(b, device=z.device) * 50
     lengths = m_len.long()
 
-    def ref(z, m, s, ld):                                                     # Modules.py:1020-1029
-        loss = torch.sum(s) + 0.5 * torch.sum(torch.exp(-2 * s) * (z - m) ** 2) - torch.sum(ld)
-        return loss / (torch.sum(lengths // 2) * 2 * 80) + 0.5 * math.log(2 * math.pi)
+    def ref(z, m, s, ld):                                                     # oracle/glow_oracle.py:mle_loss = Modules.py:1020-1029
+        from types import SimpleNamespace
+        from oracle import glow_oracle
+        return glow_oracle.mle_loss(z, m, s, ld, lengths, SimpleNamespace(num_squeeze=2, mel_dim=80))
 
     a = [t.clone().requires_grad_(True) for t in (z, mel_mean, mel_std, log_dets)]
     g = [t.clone().requires_grad_(True) for t in (z, mel_mean, mel_std, log_dets)]

@@ -78,6 +78,9 @@ SIGNATURES = {
     "glow_flow_prepare": (_I, [_PCFG, _P, _P, _I, _P, _P, _P]),
     "glow_flow_forward": (_I, [_PCALL, _P, _P, _P]),
     "glow_flow_reverse": (_I, [_PCALL, _P, _P, _F]),
+    "glow_flow_pack_rows": (_I, [_PCALL, _P, _P]),
+    "glow_actnorm_stats": (_I, [_P, _P, _I, _I, _P, _P]),
+    "glow_flow_block_forward": (_I, [_PCALL, _I, _P, _P]),
     "glow_flow_backward": (_I, [_PCALL, _P, _P, _P, _P, _P]),
     "glow_flow_backward_params": (_I, [_PCALL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_flow_param_grads": (_I, [_PCFG, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
@@ -168,6 +171,34 @@ def step_counter_ptr(device):
     return None if t is None else t.data_ptr()
 
 
+# ---- keeping cache-owned objects alive for captured CUDA graphs ----------------------------------
+# A captured graph holds RAW POINTERS to whatever the step touched: workspaces, row maps, token rows, length
+# tensors.  Those live in size-bounded caches (FlowPlan._ws, flow._ROWMAP_CACHE, rows._CACHE, _DEV_INTS below)
+# that evict when other geometries come by -- after which a replay would read and write freed memory.  While a
+# `capture_keepalive()` block is active every cache hands the objects it returns to the block's list as well; the
+# owner of the graph keeps that list for as long as the graph lives.
+_KEEPALIVE = []
+
+
+class capture_keepalive:
+    def __init__(self):
+        self.objects = []
+
+    def __enter__(self):
+        _KEEPALIVE.append(self.objects)
+        return self.objects
+
+    def __exit__(self, *exc):
+        _KEEPALIVE.remove(self.objects)
+        return False
+
+
+def keepalive(obj):
+    for lst in _KEEPALIVE:
+        lst.append(obj)
+    return obj
+
+
 # ---- small host lists -> cached device tensors ---------------------------------------------
 # Lengths come from the host collater; turning them into device tensors is an H2D copy from
 # pageable memory, which is a sync point and illegal inside CUDA-graph capture.  Steps that see
@@ -182,7 +213,7 @@ def device_ints(values, dtype, device):
         if len(_DEV_INTS) > 512:
             _DEV_INTS.clear()
         t = _DEV_INTS[key] = torch.tensor(list(key[0]), dtype=dtype).to(device)
-    return t
+    return keepalive(t)
 
 
 def side_join(device):

@@ -57,5 +57,6 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr int kNumSMs = 148;   // B200
+constexpr int kMaxDevices = 64;  // per-device tables (handles, side streams, function attributes)
 
 }  // namespace glow

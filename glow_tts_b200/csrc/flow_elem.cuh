@@ -65,6 +65,69 @@ pack_rows_kernel(const float *__restrict__ mel, int T, RowMap rm, float *__restr
     }
 }
 
+// ActNorm + 4x4 mix of ONE block applied to raw packed rows (the stand-alone form of what pack_rows_kernel and the
+// End epilogue do fused): X [rows_pad,160] -> Y, YA.  Used by the data-dependent init (glow_flow_block_forward),
+// where block k's ActNorm parameters only exist once block k-1's raw output has been seen.
+// One thread per (row, channel group).
+template <typename ActT>
+static __global__ void __launch_bounds__(256)
+mix_rows_kernel(const float *__restrict__ X, const int32_t *__restrict__ row_utt, int rows_pad, float *__restrict__ Y,
+                ActT *__restrict__ YA, const float *__restrict__ mix_scale, const float *__restrict__ mix_bias,
+                const float *__restrict__ mix_w)
+{
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= (size_t)rows_pad * (kC / 4)) return;
+    const int row = (int)(e / (kC / 4)), g = (int)(e % (kC / 4));
+    const bool m = row_utt[row] >= 0;
+    float u[4], out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = group_channel(g, i);
+        u[i] = mix_bias[ch] + mix_scale[ch] * X[(size_t)row * kC + ch];
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        out[o] = m ? mix_w[o * 4] * u[0] + mix_w[o * 4 + 1] * u[1] + mix_w[o * 4 + 2] * u[2] + mix_w[o * 4 + 3] * u[3] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = group_channel(g, i);
+        Y[(size_t)row * kC + ch] = out[i];
+        if (ch < kCh) stf(YA + (size_t)row * kCh + ch, out[i]);
+    }
+}
+
+// Masked per-channel sums for ActNorm's data-dependent init (Modules.py:698-711): out[0][c] = number of valid rows,
+// out[1][c] = sum x, out[2][c] = sum x^2 over rows with row_utt >= 0.  grid = channels / 8 CTAs of 256 threads
+// (32 row lanes x 8 channels); fixed summation order, so every run (and every rank holding the same rows) gets the
+// same bits.  Sums are carried in double: one-time work, and E[x^2] - E[x]^2 cancels.
+static __global__ void __launch_bounds__(256)
+actnorm_stats_kernel(const float *__restrict__ X, const int32_t *__restrict__ row_utt, int rows_pad, int channels,
+                     float *__restrict__ out)
+{
+    __shared__ double s_sum[32][8], s_sq[32][8];
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane_r = tid >> 3, cc = tid & 7, c = blockIdx.x * 8 + cc;
+    double sum = 0.0, sq = 0.0;
+    int cnt = 0;
+    for (int r = lane_r; r < rows_pad; r += 32) {
+        if (row_utt[r] < 0) continue;
+        const double v = (double)X[(size_t)r * channels + c];
+        sum += v; sq += v * v; ++cnt;
+    }
+    s_sum[lane_r][cc] = sum; s_sq[lane_r][cc] = sq;
+    if (cc == 0) s_cnt[lane_r] = cnt;
+    __syncthreads();
+    if (tid < 8) {
+        double a = 0.0, b = 0.0;
+        int n = 0;
+        for (int i = 0; i < 32; ++i) { a += s_sum[i][tid]; b += s_sq[i][tid]; n += s_cnt[i]; }
+        const int ch = blockIdx.x * 8 + tid;
+        out[ch] = (float)n;
+        out[channels + ch] = (float)a;
+        out[2 * channels + ch] = (float)b;
+    }
+}
+
 // Unsqueeze (Modules.py:914-924) + unpack: rows [rows_pad,160] -> out [B,80,T]; every
 // element of `out` is written (zeros / `fill` beyond each utterance's length).
 // grid = (ceil(T/64), B).

@@ -239,6 +239,36 @@ int glow_flow_forward(const glow_flow_call *call, const float *mel, float *z, fl
     return flow_forward_bf16(make_ctx<__nv_bfloat16>(call), mel, call->t_max, z, logdet, call->precision == GLOW_BF16);
 }
 
+int glow_flow_pack_rows(const glow_flow_call *call, const float *mel, float *x_rows)
+{
+    int rc = check_call(call, false);
+    if (rc) return rc;
+    GLOW_REQUIRE(mel && x_rows, GLOW_ERR_INVALID, "flow_pack_rows: null pointer");
+    const RowMap rows{call->row_utt, call->row_t, call->utt_off, call->utt_len, call->rows_pad, call->batch};
+    return flow_pack_raw(rows, mel, call->t_max, x_rows, (cudaStream_t)call->stream);
+}
+
+int glow_actnorm_stats(const float *x_rows, const int32_t *row_utt, int rows_pad, int channels, float *out,
+                       glow_stream_t stream)
+{
+    GLOW_REQUIRE(x_rows && row_utt && out, GLOW_ERR_INVALID, "actnorm_stats: null pointer");
+    GLOW_REQUIRE(rows_pad > 0 && channels > 0 && channels % 8 == 0, GLOW_ERR_INVALID,
+                 "actnorm_stats: rows_pad=%d channels=%d (channels must be a positive multiple of 8)", rows_pad, channels);
+    return actnorm_stats(x_rows, row_utt, rows_pad, channels, out, (cudaStream_t)stream);
+}
+
+int glow_flow_block_forward(const glow_flow_call *call, int block, const float *x_rows, float *z_rows)
+{
+    int rc = check_call(call, false);
+    if (rc) return rc;
+    GLOW_REQUIRE(x_rows && z_rows && x_rows != z_rows, GLOW_ERR_INVALID, "flow_block_forward: null or aliased rows");
+    GLOW_REQUIRE(block >= 0 && block < call->cfg.blocks, GLOW_ERR_INVALID, "flow_block_forward: block=%d of %d", block,
+                 call->cfg.blocks);
+    GLOW_REQUIRE(!call->training, GLOW_ERR_INVALID, "flow_block_forward: uses the inference workspace (training = 0)");
+    if (call->precision == GLOW_F32) return flow_block_forward_f32(make_ctx<float>(call), block, x_rows, z_rows);
+    return flow_block_forward_bf16(make_ctx<__nv_bfloat16>(call), block, x_rows, z_rows, call->precision == GLOW_BF16);
+}
+
 int glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel, float fill)
 {
     int rc = check_call(call, false);

@@ -82,12 +82,17 @@ int flow_forward_f32(const FlowCtx<float> &c, const float *mel, int T, float *z,
 int flow_reverse_f32(const FlowCtx<float> &c, const float *z, int T, float *mel, float fill);
 int flow_backward_f32(const FlowCtx<float> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
                       float *dmel, float *dspk);
+int flow_block_forward_f32(const FlowCtx<float> &c, int k, const float *X, float *Z);
 // bf16 tcgen05 path (flow_tc.cu)
 // (tc = true) and the same bf16 storage on the CUDA-core GEMM (tc = false, cross-check only)
 int flow_forward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *mel, int T, float *z, float *logdet, bool tc);
 int flow_reverse_bf16(const FlowCtx<__nv_bfloat16> &c, const float *z, int T, float *mel, float fill, bool tc);
 int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, const float *dlogdet, float *dwpack,
                        float *dmel, float *dspk, bool tc);
+int flow_block_forward_bf16(const FlowCtx<__nv_bfloat16> &c, int k, const float *X, float *Z, bool tc);
+// raw squeezed rows of a [B,80,T] tensor (no ActNorm / mix): the input of block 0 as its ActNorm sees it
+int flow_pack_raw(const RowMap &rows, const float *mel, int T, float *X, cudaStream_t st);
+int actnorm_stats(const float *X, const int32_t *row_utt, int rows_pad, int channels, float *out, cudaStream_t st);
 
 // Side stream for the weight-gradient GEMMs (flow_wgrad.cu): one per device, with fork / done
 // events per block parity.  Works under CUDA-graph capture (the event waits pull it into the capture).

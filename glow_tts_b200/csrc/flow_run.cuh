@@ -169,6 +169,41 @@ int flow_forward_impl(const FlowCtx<ActT> &c, const float *mel, int T, float *z,
     return GLOW_OK;
 }
 
+// ------------------------------------------------- one block, raw in -> raw out --
+// ActNorm data-dependent init (Modules.py:685-711): block k's statistics are those of block k-1's RAW output, so
+// the init walks the decoder once, block by block: stats of X (glow_actnorm_stats) -> parameters -> this call.
+// X, Z: packed rows [rows_pad,160] fp32 (raw = before / after the block, no neighbouring block's ActNorm fused in).
+template <typename ActT, bool FAST, class Ops>
+int flow_block_forward_impl(const FlowCtx<ActT> &c, int k, const float *X, float *Z)
+{
+    const int R = c.rows.rows_pad, B = c.rows.batch;
+    float *SKIP = c.ws_f32 + c.wl.skip;
+    if (c.spk != nullptr) {
+        spk_bias_kernel<<<dim3(c.cfg.blocks * kLayers, B), kG, 0, c.st>>>(c.spk, c.cfg.spk_dim, c.wpack, c.bp.total,
+                                                                         c.bp, B, c.ws_f32 + c.wl.spkb);
+        GLOW_CHECK_LAUNCH("spk_bias_kernel");
+    }
+    Bufs<ActT> b = block_bufs(c, k);
+    const float *wpk = c.wpack + (size_t)k * c.bp.total;
+    const size_t n = (size_t)R * (kC / 4);
+    mix_rows_kernel<ActT><<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(X, c.rows.row_utt, R, b.Y, b.YA, wpk + c.bp.an_scale,
+                                                                       wpk + c.bp.an_bias, wpk + c.bp.w);
+    GLOW_CHECK_LAUNCH("mix_rows_kernel");
+    GLOW_TRY(Ops::start(c, k, b));
+    for (int i = 0; i < kLayers; ++i) GLOW_TRY(Ops::layer(c, k, i, b, SKIP));
+    EpiEnd<ActT, FAST> e;
+    e.bias = wpk + c.bp.end_b;
+    e.Y = b.Y;
+    e.OUTS = nullptr;
+    e.rowld = nullptr;
+    e.Ynext = Z;
+    e.YAnext = nullptr;
+    e.mix_scale = e.mix_bias = e.mix_w = nullptr;
+    e.row_utt = c.rows.row_utt;
+    e.reverse = 0;
+    return Ops::end(c, k, b, e);
+}
+
 // ------------------------------------------------------------- reverse -------
 // Modules.py:303,664: blocks 11..0, inside a block coupling^-1 -> mix^-1 -> ActNorm^-1.
 template <typename ActT, bool FAST, class Ops>

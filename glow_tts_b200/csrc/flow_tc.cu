@@ -24,4 +24,10 @@ int flow_backward_bf16(const FlowCtx<__nv_bfloat16> &c, const float *dz, int T, 
     return flow_backward_impl<__nv_bfloat16, true, OpsBf16Simt>(c, dz, T, dlogdet, dwpack, dmel, dspk);
 }
 
+int flow_block_forward_bf16(const FlowCtx<__nv_bfloat16> &c, int k, const float *X, float *Z, bool tc)
+{
+    if (tc) return flow_block_forward_impl<__nv_bfloat16, true, OpsTc>(c, k, X, Z);
+    return flow_block_forward_impl<__nv_bfloat16, true, OpsBf16Simt>(c, k, X, Z);
+}
+
 }  // namespace glow

@@ -386,10 +386,14 @@ int gemm_tc3(const TcA &a, const __nv_bfloat16 *Wslab, const int32_t *row_utt, i
     using Cfg = TcCfg<N, BN, KP, NP, LD, TAPS, DIR, KS>;
     GLOW_REQUIRE(rows_pad % 128 == 0, GLOW_ERR_INVALID, "%s: tensor-core GEMM rows=%d", name, rows_pad);
     auto kern = tc_gemm3_kernel<Cfg, N, BN, KP, NP, LD, TAPS, DIR, KS, AMODE, Epi>;
-    static bool attr_set = false;                  // per template instantiation
-    if (!attr_set) {
+    // cudaFuncSetAttribute is per device: one flag per (template instantiation, device), so a process that drives
+    // several GPUs sets it on each of them
+    static bool attr_set[kMaxDevices] = {};
+    int dev = 0;
+    GLOW_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
         GLOW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
+        if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
     }
     const int n_items = (rows_pad / 128) * Cfg::kSlices;
     const int grid = n_items < kNumSMs ? n_items : kNumSMs;

@@ -13,7 +13,7 @@
 namespace glow {
 
 static std::mutex g_handle_mu;
-static cublasHandle_t g_handles[16][2] = {{nullptr}};
+static cublasHandle_t g_handles[kMaxDevices][2] = {{nullptr}};
 
 // lane 0: everything issued from the decoder's streams; lane 1: the encoder's side stream.  The two run
 // concurrently (the encoder's backward overlaps the decoder's), so each has its own handle (cuBLAS
@@ -22,7 +22,7 @@ static int get_handle(cublasHandle_t *out, int lane)
 {
     int dev = 0;
     GLOW_CHECK_CUDA(cudaGetDevice(&dev));
-    GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
+    GLOW_REQUIRE(dev >= 0 && dev < kMaxDevices, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
     std::lock_guard<std::mutex> lock(g_handle_mu);
     if (g_handles[dev][lane] == nullptr) {
         cublasStatus_t s = cublasCreate(&g_handles[dev][lane]);
@@ -32,14 +32,14 @@ static int get_handle(cublasHandle_t *out, int lane)
     return GLOW_OK;
 }
 
-static SideStream g_side[16];
-static bool g_side_init[16] = {false};
+static SideStream g_side[kMaxDevices];
+static bool g_side_init[kMaxDevices] = {false};
 
 int side_stream(SideStream **out)
 {
     int dev = 0;
     GLOW_CHECK_CUDA(cudaGetDevice(&dev));
-    GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
+    GLOW_REQUIRE(dev >= 0 && dev < kMaxDevices, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
     std::lock_guard<std::mutex> lock(g_handle_mu);
     if (!g_side_init[dev]) {
         SideStream &s = g_side[dev];
@@ -73,7 +73,7 @@ int side_stream(SideStream **out)
 // GEMMs are DEFERRED into one launch (wgrad_flush: a decoder block's 13 gradients in one kernel).
 constexpr int kMaxSplitBatch = 96;
 constexpr int kMaxSplitJobs = 16;
-constexpr int kSplitSlots = 1024;
+constexpr int kSplitSlots = 8192;    // cached call sites: ~160 per captured train-step graph (one graph per geometry bucket)
 constexpr int kSplitTemp = 64;                                          // slots [0, kSplitTemp): refilled on every use
 constexpr size_t kSplitFloats = (size_t)12 << 20;                       // 48 MB of fp32 partials (one decoder block: ~11 M)
 
@@ -112,13 +112,13 @@ struct SplitScratch {
     SplitJobs pending;
     std::unordered_map<SplitKey, int, SplitKeyHash> *slots;
 };
-static SplitScratch g_split[16][2];
-static bool g_split_init[16][2] = {{false}};
+static SplitScratch g_split[kMaxDevices][2];
+static bool g_split_init[kMaxDevices][2] = {{false}};
 
 static int lane_of(cudaStream_t st)
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
     return (g_side_init[dev] && st == g_side[dev].enc_stream) ? 1 : 0;
 }
 
@@ -126,7 +126,7 @@ static int split_scratch(SplitScratch **out, int lane)
 {
     int dev = 0;
     GLOW_CHECK_CUDA(cudaGetDevice(&dev));
-    GLOW_REQUIRE(dev >= 0 && dev < 16, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
+    GLOW_REQUIRE(dev >= 0 && dev < kMaxDevices, GLOW_ERR_UNSUPPORTED, "wgrad: device index %d", dev);
     std::lock_guard<std::mutex> lock(g_handle_mu);
     if (!g_split_init[dev][lane]) {
         SplitScratch &s = g_split[dev][lane];

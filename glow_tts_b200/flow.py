@@ -87,7 +87,7 @@ def row_map(sq_lengths, device):
         if len(_ROWMAP_CACHE) > 64:
             _ROWMAP_CACHE.clear()
         rm = _ROWMAP_CACHE[key] = RowMap(sq_lengths, device)
-    return rm
+    return _lib.keepalive(rm)
 
 
 # ---- side stream for work that is off the step's critical path ------------------------------
@@ -167,7 +167,7 @@ class FlowPlan:
                    if tag != _lib.GLOW_F32 else None)
             dwp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
             self._wpack[key] = (wp, wtc, dwp)
-        return self._wpack[key]
+        return _lib.keepalive(self._wpack[key])
 
     def prepare(self, flat_params, offsets_host, device, tag):
         wp, wtc, _ = self.wpack(device, tag)
@@ -194,7 +194,19 @@ class FlowPlan:
                   torch.zeros(max(out[2], 1), dtype=torch.float32, device=device) if training else None,
                   torch.zeros(max(out[3], 1), dtype=act_dtype, device=device) if training else None)
             self._ws[key] = ws
-        return ws
+        return _lib.keepalive(ws)
+
+    # One workspace per shape holds the activations a backward needs, so only ONE grad-enabled forward of a
+    # shape may be in flight: a second forward overwrites what the first one's backward would read.  Every
+    # forward stamps the workspace; backward refuses to run on a workspace that has been re-stamped since.
+    def stamp(self, ws):
+        self._gen = getattr(self, "_gen", 0) + 1
+        self._stamps = getattr(self, "_stamps", {})
+        self._stamps[ws[0].data_ptr()] = self._gen
+        return self._gen
+
+    def stamp_of(self, ws):
+        return getattr(self, "_stamps", {}).get(ws[0].data_ptr())
 
     def call_struct(self, rm, t_max, tag, wp, wtc, spk, ws, training, seed, device):
         c = _lib.FlowCall()
@@ -241,6 +253,7 @@ class FlowDecoderFn(torch.autograd.Function):
             rc = _lib.lib().glow_flow_forward(ctypes.byref(call), _lib.ptr(mel), _lib.ptr(z), _lib.ptr(logdet))
         _lib.check(rc, "glow_flow_forward")
         ctx.owner, ctx.rm, ctx.call, ctx.keep = owner, rm, call, (wp, wtc, ws, spk_c, flat)
+        ctx.ws_stamp = plan.stamp(ws) if training else None
         ctx.need_dmel = mel.requires_grad
         ctx.has_spk = spk is not None
         ctx.training = training
@@ -254,6 +267,11 @@ class FlowDecoderFn(torch.autograd.Function):
         owner, rm, call = ctx.owner, ctx.rm, ctx.call
         plan = owner.plan
         wp, wtc, ws, spk_c, flat = ctx.keep
+        if plan.stamp_of(ws) != ctx.ws_stamp:
+            raise _lib.GlowCoreError(
+                "flow decoder backward: the saved activations of this forward were overwritten by a later "
+                "grad-enabled forward of the same shape (one workspace per shape: run backward before the next "
+                "forward, e.g. accumulate gradients with one backward per micro-batch)")
         device = wp.device
         tag, _ = precision_tag(owner.precision)
         dz = dz.contiguous().float() if dz is not None else torch.zeros(

@@ -31,6 +31,7 @@ DEFAULTS = {
     "Speaker_Embedding": {"Type": "LUT", "Num_Speakers": 109, "Embedding_Size": 256},
     "Train": {
         "Batch_Size": 32,
+        "Train_Pattern": {"Mel_Length": {"Min": 50, "Max": 1000}, "Text_Length": {"Min": 10, "Max": 200}},
         "Learning_Rate": {"Initial": 1.0e-3, "Base": 4000},
         "ADAM": {"Beta1": 0.9, "Beta2": 0.999, "Epsilon": 1.0e-6},
         "Weight_Decay": 1.0e-6, "Gradient_Norm": 5.0,

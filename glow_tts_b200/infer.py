@@ -30,15 +30,18 @@ class GraphedInference:
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):                  # eager warm-up: weight packs, workspaces, library handles
-            for _ in range(max(1, warmup)):
-                self._call()
-        cur.wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self.mels, self.mel_lengths, self.attentions = self._call()
+        # the graph holds raw pointers into cache-owned objects (workspace, device row map): keep them alive with it
+        with _lib.capture_keepalive() as keep:
+            with torch.cuda.stream(side):                  # eager warm-up: weight packs, workspaces, library handles
+                for _ in range(max(1, warmup)):
+                    self._call()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.mels, self.mel_lengths, self.attentions = self._call()
+        self._keep = list(keep)
         self.launches_per_replay = _lib.launch_count() - before
 
     def _call(self):

@@ -10,9 +10,11 @@ the arithmetic happens:
 * ``RPR_Multihead_Attention`` core -> glow_rpr_attention_* (csrc/attention.cu)
 * ``Maximum_Path_Generater``  -> glow_mas_forward (csrc/mas.cu)
 
-Convolutions / LayerNorm of the encoder stay torch ops ("host code stays
-PyTorch", BASELINE.json north_star).  There is no CPU fallback: tensors must be
-on a CUDA device.
+* ``Encoder`` convolutions / LayerNorm (bf16 mode) -> packed-row tcgen05 convs and fused LayerNorm kernels
+  (rows.py, csrc/rows_conv.cu, csrc/rows_norm.cu); the fp32 parity mode keeps the torch ops.
+* ``log_P`` / path expansion / ``MLE_Loss`` -> csrc/align.cu
+
+There is no CPU fallback: tensors must be on a CUDA device.
 """
 import math
 import os
@@ -216,6 +218,7 @@ class Decoder(torch.nn.Module):
         self.host_lengths = None       # optional: set by the caller to skip the D2H sync
         self._prepared = None          # (wpack, wpack_tc) being prepared on the side stream (begin_prepare)
         self.device_lengths = None     # set around a call by GlowTTS.inference_device: mel lengths as a device tensor
+        self.geometry = None           # set around a call by GlowTTS.forward: geometry.StepGeometry (static row map)
         self._dev_maps = {}
         self.defer_param_grads = False  # set by train.TrainStep, which joins the side stream before the optimizer
 
@@ -272,34 +275,49 @@ class Decoder(torch.nn.Module):
 
     # ---- ActNorm data-dependent init (Modules.py:685-711) -----------------------------
     @torch.no_grad()
-    def _data_dependent_init(self, x, rm, sq_len, speakers):
-        """Block k's ActNorm statistics are those of block k-1's output, so blocks are
-        initialised in order with k-block forwards (one-time cost at step 0).  Under
-        torch.distributed the three sums are all-reduced so every rank gets the same init."""
+    def _data_dependent_init(self, x, rm, speakers):
+        """Block k's ActNorm statistics are those of block k-1's raw output, so the decoder is walked ONCE, block
+        by block, on packed rows: glow_actnorm_stats -> logs / bias (Modules.py:698-711) -> glow_flow_prepare ->
+        glow_flow_block_forward.  Under torch.distributed the three sums are all-reduced, so every rank gets the
+        same parameters (the reference has no DDP; per-rank statistics would make the replicas diverge)."""
+        import ctypes
         flows = self.layer_Dict["Flows"]
-        b, c, t = x.shape
-        t2 = (t // 2) * 2
-        tmask = (torch.arange(t2 // 2, device=x.device)[None, :] <
-                 torch.as_tensor(sq_len, device=x.device)[:, None]).float()            # [B,T']
-        for k, blk in enumerate(flows):
-            an = blk.layers[0]
-            if an.initialized:
-                continue
-            if k == 0:
-                cur = x[:, :, :t2] * tmask.repeat_interleave(2, dim=1).unsqueeze(1)
-            else:
-                cur = _FlowPrefix.run(self, k, rm, x, speakers)
-            sq = cur[:, :, :t2].reshape(b, c, t2 // 2, 2).permute(0, 3, 1, 2).reshape(b, 2 * c, t2 // 2)
-            m = tmask.unsqueeze(1)
-            sums = torch.stack([m.sum() .expand(2 * c), (sq * m).sum(dim=(0, 2)), (sq * sq * m).sum(dim=(0, 2))])
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                torch.distributed.all_reduce(sums)
-            mean = sums[1] / sums[0]
-            var = sums[2] / sums[0] - mean ** 2
-            half_log_var = 0.5 * torch.log(torch.clamp_min(var, 1e-7))
-            an.logs.data.copy_((-half_log_var).view_as(an.logs))
-            an.bias.data.copy_((-mean * torch.exp(-half_log_var)).view_as(an.bias))
-            an.initialized = True
+        dev = x.device
+        plan = self.plan
+        tag, act_dtype = _flow.precision_tag(self.precision)
+        flat, offs = self.flat_params()
+        L = _lib.lib()
+        c = 2 * self.mel_dim
+        with torch.cuda.device(dev):
+            ws = plan.workspace(rm, dev, act_dtype, False)
+            spk = speakers.contiguous().float() if speakers is not None else None
+            xc = x.contiguous().float()
+            cur = torch.zeros((rm.rows_pad, c), dtype=torch.float32, device=dev)
+            nxt = torch.zeros_like(cur)
+            sums = torch.empty(3 * c, dtype=torch.float32, device=dev)
+            wp, wtc = plan.prepare(flat, offs, dev, tag)
+            call = plan.call_struct(rm, xc.shape[2], tag, wp, wtc, spk, ws, False, 0, dev)
+            _lib.check(L.glow_flow_pack_rows(ctypes.byref(call), _lib.ptr(xc), _lib.ptr(cur)), "glow_flow_pack_rows")
+            for k, blk in enumerate(flows):
+                an = blk.layers[0]
+                if not an.initialized:
+                    _lib.check(L.glow_actnorm_stats(_lib.ptr(cur), rm.row_utt.data_ptr(), rm.rows_pad, c, _lib.ptr(sums),
+                                                    _lib.stream_ptr(dev)), "glow_actnorm_stats")
+                    s3 = sums.view(3, c).double()
+                    if torch.distributed.is_available() and torch.distributed.is_initialized():
+                        torch.distributed.all_reduce(s3)
+                    mean = s3[1] / s3[0]
+                    var = s3[2] / s3[0] - mean ** 2
+                    half_log_var = 0.5 * torch.log(torch.clamp_min(var, 1e-7))
+                    an.logs.data.copy_((-half_log_var).view_as(an.logs))
+                    an.bias.data.copy_((-mean * torch.exp(-half_log_var)).view_as(an.bias))
+                    an.initialized = True
+                    wp, wtc = plan.prepare(flat, offs, dev, tag)      # exp(logs), bias of block k -> packed weights
+                if k + 1 < len(flows) and not all(b.layers[0].initialized for b in flows[k + 1:]):
+                    call.stream = torch.cuda.current_stream(dev).cuda_stream
+                    _lib.check(L.glow_flow_block_forward(ctypes.byref(call), k, _lib.ptr(cur), _lib.ptr(nxt)),
+                               "glow_flow_block_forward")
+                    cur, nxt = nxt, cur
 
     def _device_row_map(self, batch, sq_max, device):
         key = (batch, sq_max, str(device))
@@ -307,7 +325,7 @@ class Decoder(torch.nn.Module):
             if len(self._dev_maps) > 16:
                 self._dev_maps.clear()
             self._dev_maps[key] = _flow.DeviceRowMap(batch, sq_max, device)
-        return self._dev_maps[key]
+        return _lib.keepalive(self._dev_maps[key])
 
     # ---- forward -----------------------------------------------------------------------
     def forward(self, x, mask, speakers=None, prosodies=None, pitches=None, reverse=False):
@@ -327,6 +345,13 @@ class Decoder(torch.nn.Module):
             sq_dev = torch.clamp(self.device_lengths.to(torch.int64), max=t2) // 2
             rm = self._device_row_map(b, t2 // 2, x.device).update(sq_dev)
             out_mask = (torch.arange(t2, device=x.device)[None, None, :] < (2 * sq_dev)[:, None, None]).to(x.dtype)
+        elif self.geometry is not None:
+            # bucketed training (geometry.py): the row map lives in fixed device buffers refreshed before every step
+            geo = self.geometry
+            if reverse or t2 != geo.t_mel:
+                raise _lib.GlowCoreError("StepGeometry is for the forward direction on [B, 80, %d] inputs" % geo.t_mel)
+            rm = geo.dec_rm
+            out_mask = (torch.arange(t2, device=x.device)[None, None, :] < (2 * geo.sq64)[:, None, None]).to(x.dtype)
         else:
             lens = self.host_lengths if self.host_lengths is not None else _host_lengths(mask=mask)
             sq_len = [min(n, t2) // 2 for n in lens]
@@ -340,35 +365,13 @@ class Decoder(torch.nn.Module):
                 y = _flow.flow_reverse(self, rm, xin, speakers, 0.0)
             return y.to(x.dtype), None, out_mask
         if not all(blk.layers[0].initialized for blk in self.layer_Dict["Flows"]):
-            self._data_dependent_init(xin.float(), rm, sq_len, speakers)
+            self._data_dependent_init(xin.float(), rm, speakers)
         seed = 0
         if self.training and self.dropout > 0:
             self._step += 1
             seed = (int(torch.initial_seed()) * 0x9E3779B1 + self._step * 0x85EBCA77) & 0x7FFFFFFFFFFFFFFF or 1
         z, logdet = _flow.FlowDecoderFn.apply(self, rm, xin, speakers, seed, *self.slot_params())
         return z.to(x.dtype), logdet, out_mask
-
-
-class _FlowPrefix:
-    """Output of the first k blocks (used only by the data-dependent init)."""
-
-    @staticmethod
-    def run(dec, k, rm, x, speakers):
-        import ctypes
-        plan = dec.plan_for(k)
-        tag, act_dtype = _flow.precision_tag(dec.precision)
-        flat, offs = dec.flat_params()
-        with torch.cuda.device(x.device):
-            wp, wtc = plan.prepare(flat, offs, x.device, tag)
-            ws = plan.workspace(rm, x.device, act_dtype, False)
-            spk = speakers.contiguous().float() if speakers is not None else None
-            call = plan.call_struct(rm, x.shape[2], tag, wp, wtc, spk, ws, False, 0, x.device)
-            xc = x.contiguous().float()
-            z = torch.empty_like(xc)
-            ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-            rc = _lib.lib().glow_flow_forward(ctypes.byref(call), _lib.ptr(xc), _lib.ptr(z), _lib.ptr(ld))
-        _lib.check(rc, "glow_flow_forward")
-        return z
 
 
 # --------------------------------------------------------------------------- #
@@ -509,11 +512,11 @@ class Encoder(torch.nn.Module):
         self.layer_Dict["Project"] = torch.nn.Conv1d(e.Channels, h.Sound.Mel_Dim * 2, 1)
         self.layer_Dict["Duration_Predictor"] = Duration_Predictor()
 
-    def forward(self, x, mask, speakers=None, prosodies=None, lengths=None, host_lengths=None):
+    def forward(self, x, mask, speakers=None, prosodies=None, lengths=None, host_lengths=None, token_rows=None):
         _lib.require_cuda(mask, "Encoder mask")
         # bf16 mode with the sentence lengths known on the host: packed-row encoder on the tcgen05 convs
-        if self.precision == "bf16" and host_lengths is not None and self.rows_supported:
-            return self._forward_rows(x, mask, speakers, lengths, host_lengths)
+        if self.precision == "bf16" and (host_lengths is not None or token_rows is not None) and self.rows_supported:
+            return self._forward_rows(x, mask, speakers, lengths, host_lengths, token_rows)
         # fp32 mode is the parity mode: keep cuDNN from silently using TF32 for the convs
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "fp32"):
             return self._forward(x, mask, speakers, lengths)
@@ -541,7 +544,7 @@ class Encoder(torch.nn.Module):
         return ((int(torch.initial_seed()) * 0x9E3779B1 + self._calls * 0x85EBCA77 + site * 0xC2B2AE3D + 1)
                 & 0x7FFFFFFFFFFFFFFF) or 1
 
-    def _forward_rows(self, tokens, mask, speakers, lengths, host_lengths):
+    def _forward_rows(self, tokens, mask, speakers, lengths, host_lengths, token_rows=None):
         """Modules.py:262-284 on packed token rows [rows, C] (rows.py): same arithmetic at every real
         token; guard rows stand in for the padding the reference masks away.  Every op writes guard
         rows as zeros, so convs need no separate `* mask` pass."""
@@ -549,7 +552,7 @@ class Encoder(torch.nn.Module):
         dev = tokens.device
         h = _hp().Encoder
         self._calls = getattr(self, "_calls", 0) + 1
-        tr = _rows.token_rows(host_lengths, tokens.shape[1], dev)
+        tr = token_rows if token_rows is not None else _rows.token_rows(host_lengths, tokens.shape[1], dev)
         pk = self._packed_weights(dev)
         pk.pack()                                  # every conv weight of the encoder -> bf16 slab images, one launch
         tok = tokens.reshape(-1).index_select(0, tr.src_idx)
@@ -671,18 +674,31 @@ class GlowTTS(torch.nn.Module):
         return (torch.arange(n, device=device)[None, :] < t[:, None]).unsqueeze(1).float()
 
     def forward(self, tokens, token_lengths, mels, mel_lengths, speakers=None, mels_for_ge2e=None, pitches=None,
-                host_token_lengths=None, host_mel_lengths=None):
+                host_token_lengths=None, host_mel_lengths=None, geometry=None):
+        """geometry: a geometry.StepGeometry already `update`d for this batch -- every length-derived tensor then
+        comes from its fixed device buffers (tokens must be [B, geometry.t_text], mels [B, 80, geometry.t_mel]), so
+        the call is the same stream of launches for every batch of the bucket (train.GraphedTrainStep)."""
         _lib.require_cuda(mels, "mels")
         d = self.layer_Dict
         dev = mels.device
-        tl = host_token_lengths if host_token_lengths is not None else _host_lengths(lengths=token_lengths)
-        ml = host_mel_lengths if host_mel_lengths is not None else _host_lengths(lengths=mel_lengths)
+        geo = geometry
+        if geo is not None:
+            geo.derive()
+            tl, ml = geo.host_tl, geo.host_ml
+            if tokens.shape[1] != geo.t_text or mels.shape[2] != geo.t_mel:
+                raise ValueError("geometry expects tokens [B,%d] and mels [B,80,%d]" % (geo.t_text, geo.t_mel))
+        else:
+            tl = host_token_lengths if host_token_lengths is not None else _host_lengths(lengths=token_lengths)
+            ml = host_mel_lengths if host_mel_lengths is not None else _host_lengths(lengths=mel_lengths)
         assert all(n % self.num_squeeze == 0 for n in ml), "Mel lengths must be diviable by Num_Squeeze."
         spk = d["LUT"](speakers) if "LUT" in d else None
-        token_masks = self._masks_from_host(tl, dev)[:, :, :tokens.shape[1]]
-        mel_masks = self._masks_from_host(ml, dev)
-        t_len = _lib.device_ints(tl, torch.int32, dev)
-        m_len = _lib.device_ints(ml, torch.int32, dev)
+        if geo is not None:
+            token_masks, mel_masks, t_len, m_len = geo.token_masks, geo.mel_masks, geo.tl32, geo.ml32
+        else:
+            token_masks = self._masks_from_host(tl, dev)[:, :, :tokens.shape[1]]
+            mel_masks = self._masks_from_host(ml, dev)
+            t_len = _lib.device_ints(tl, torch.int32, dev)
+            m_len = _lib.device_ints(ml, torch.int32, dev)
 
         dec = d["Decoder"]
         if torch.is_grad_enabled():
@@ -694,12 +710,13 @@ class GlowTTS(torch.nn.Module):
             enc.wait_stream(cur)
         with torch.cuda.stream(enc):
             mean, log_std, log_dur, token_masks = d["Encoder"](tokens[:, :token_masks.shape[2]], token_masks, spk,
-                                                               None, lengths=t_len, host_lengths=tl)
-        dec.host_lengths = ml
+                                                               None, lengths=t_len, host_lengths=tl,
+                                                               token_rows=geo.tok if geo is not None else None)
+        dec.host_lengths, dec.geometry = ml, geo
         try:
-            z, log_dets, mel_masks = dec(mels[:, :, :max(ml)], mel_masks, spk, None, None)
+            z, log_dets, mel_masks = dec(mels if geo is not None else mels[:, :, :max(ml)], mel_masks, spk, None, None)
         finally:
-            dec.host_lengths = None
+            dec.host_lengths = dec.geometry = None
         if overlap:
             cur.wait_stream(enc)
             for t in (mean, log_std, log_dur, token_masks):

@@ -63,7 +63,7 @@ def token_rows(lengths, t_max, device):
         if len(_CACHE) > 64:
             _CACHE.clear()
         tr = _CACHE[key] = TokenRows(key[0], t_max, device)
-    return tr
+    return _lib.keepalive(tr)
 
 
 def _call(tr, cin, cout, taps, device, relu=False, p=0.0, seed=0):

@@ -117,6 +117,8 @@ class _AttnRowsFn(torch.autograd.Function):
 
 
 class RPR_Multihead_Attention(torch.nn.Module):
+    _built = 0
+
     def __init__(self, query_channels, calc_channels, out_channels, num_heads,
                  relative_postion_clipping_distance=None, share_relative_postion_weight=True,
                  proximal_bias=False, block_mask_length=None, dropout_rate=0.0,
@@ -133,6 +135,10 @@ class RPR_Multihead_Attention(torch.nn.Module):
         self.relative_postion_clipping_distance = relative_postion_clipping_distance
         self.dropout_rate = float(dropout_rate)
         self._calls = 0
+        # position of this module among the attention modules built so far: a deterministic stand-in for the module's
+        # identity in the dropout seed (id(self) would differ from run to run under one torch.manual_seed)
+        self._index = RPR_Multihead_Attention._built
+        RPR_Multihead_Attention._built += 1
         self.layer_Dict = torch.nn.ModuleDict()
         self.layer_Dict["Query"] = torch.nn.Conv1d(query_channels, calc_channels, 1)
         self.layer_Dict["Key"] = torch.nn.Conv1d(key_channels or query_channels, calc_channels, 1)
@@ -162,7 +168,7 @@ class RPR_Multihead_Attention(torch.nn.Module):
         if not (self.training and self.dropout_rate > 0):
             return 0
         self._calls += 1
-        return ((int(torch.initial_seed()) * 0x2545F491 + self._calls * 0x9E3779B1 + id(self) % 65521)
+        return ((int(torch.initial_seed()) * 0x2545F491 + self._calls * 0x9E3779B1 + (self._index % 65521) * 0x632BE5AB)
                 & 0x7FFFFFFFFFFFFFFF) or 1
 
     def forward(self, queries, keys=None, values=None, masks=None, lengths=None, need_alignments=True):

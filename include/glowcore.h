@@ -267,6 +267,23 @@ int    glow_flow_param_grads(const glow_flow_config *cfg, const float *params,
                              const int32_t *utt_len, int batch, float *grads,
                              glow_stream_t stream);
 
+/*
+ * ActNorm data-dependent initialisation (replaces Activation_Norm.initialize, Modules.py:698-711; SURVEY 8b
+ * "glow_actnorm_stats").  The reference initialises block k from the first batch as it passes through: its
+ * statistics are those of block k-1's output.  Here the same walk is three calls per block, so that a
+ * data-parallel host can all-reduce the sums between them:
+ *   glow_flow_pack_rows      mel [batch,80,t_max] -> x_rows [rows_pad,160] f32: the squeezed, packed input of block 0
+ *   glow_actnorm_stats       out[0][c] = number of valid rows, out[1][c] = sum x, out[2][c] = sum x^2 over rows with
+ *                            row_utt >= 0 (out: 3*channels f32, channels % 8 == 0; fixed summation order)
+ *   glow_flow_block_forward  x_rows (raw input of block k) -> z_rows (raw output of block k), with block k's
+ *                            ActNorm / 4x4 / coupling parameters taken from call->wpack (re-run glow_flow_prepare after
+ *                            writing the new logs / bias).  Uses the inference workspace (training = 0).
+ */
+int    glow_flow_pack_rows(const glow_flow_call *call, const float *mel, float *x_rows);
+int    glow_actnorm_stats(const float *x_rows, const int32_t *row_utt, int rows_pad, int channels,
+                          float *out, glow_stream_t stream);
+int    glow_flow_block_forward(const glow_flow_call *call, int block, const float *x_rows, float *z_rows);
+
 /* ------------------------------------------------------------------------ *
  * Relative-position multi-head self-attention core
  * replaces: RPR_MHA.py:95-128 Calc_Attention and its helpers :131-165

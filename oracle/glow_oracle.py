@@ -67,7 +67,7 @@ class OracleHP:
 def length_mask(lengths, max_len=None):
     """Modules.py:206-211 Mask_Generate -> [B,1,T] float."""
     max_len = int(max_len if max_len is not None else int(lengths.max()))
-    return (torch.arange(max_len)[None, :] < lengths[:, None]).unsqueeze(1).float()
+    return (torch.arange(max_len, device=lengths.device)[None, :] < lengths[:, None]).unsqueeze(1).float()
 
 
 def wn_weight(sd, prefix):
@@ -130,7 +130,7 @@ def group_channel_index(channels, split=4):
 def inv1x1(x, mask, weight, reverse=False, split=4):
     """Modules.py:727-758 as an explicit per-group 4x4 mix."""
     b, c, t = x.shape
-    idx = group_channel_index(c, split)                      # [split, groups]
+    idx = group_channel_index(c, split).to(x.device)         # [split, groups]
     w = torch.inverse(weight) if reverse else weight          # :743 / :746
     grouped = x[:, idx.reshape(-1)].view(b, split, c // split, t)
     mixed = torch.einsum("ok,bkgt->bogt", w, grouped)
@@ -206,15 +206,36 @@ def decoder(sd, x, mask, hp, spk=None, reverse=False, training=False,
     return x, total, mask
 
 
+def decoder_ddi(sd, x, mask, hp, spk=None, prefix="layer_Dict.Decoder.layer_Dict"):
+    """Decoder.forward (Modules.py:298-309) on a model whose Activation_Norm layers are all uninitialised: each
+    block's first call sets logs / bias from the statistics of ITS input (Modules.py:685-711), i.e. of the previous
+    block's output under the freshly initialised parameters.  Writes the new logs / bias into `sd` and returns
+    (z, logdet, logs [blocks, C], bias [blocks, C])."""
+    with torch.no_grad():
+        x, m = squeeze2(x, mask, hp.num_squeeze)
+        total, all_logs, all_bias = None, [], []
+        for i in range(hp.dec_stack):
+            p = f"{prefix}.Flows.{i}"
+            logs, bias = actnorm_ddi(x, m)
+            sd[f"{p}.layers.0.logs"] = logs
+            sd[f"{p}.layers.0.bias"] = bias
+            all_logs.append(logs.view(-1))
+            all_bias.append(bias.view(-1))
+            x, ld = flow_block(sd, p, x, m, hp, spk, False, False)
+            total = ld if total is None else total + ld
+        x, _ = unsqueeze2(x, m, hp.num_squeeze)
+    return x, total, torch.stack(all_logs), torch.stack(all_bias)
+
+
 # --------------------------------------------------------------------------- #
 # relative-position attention (RPR_MHA.py:69-165) -- banded formulation
 # --------------------------------------------------------------------------- #
-def rel_band(t, window):
+def rel_band(t, window, device=None):
     """[T,T] long index j-i+window inside the band |j-i|<=window, and the band mask.
     RPR_MHA.py:131-165 realise this with zero-padded embeddings + skew views:
     positions outside the window contribute exactly 0 (padded, not clipped)."""
-    i = torch.arange(t).view(-1, 1)
-    j = torch.arange(t).view(1, -1)
+    i = torch.arange(t, device=device).view(-1, 1)
+    j = torch.arange(t, device=device).view(1, -1)
     d = j - i
     return (d + window).clamp(0, 2 * window), (d.abs() <= window)
 
@@ -232,7 +253,7 @@ def rpr_attention(sd, p, x, attn_mask, hp, training=False):
     v = v.view(b, hds, d, t).transpose(2, 3)
     scale = 1.0 / math.sqrt(d)
     scores = (q @ k.transpose(2, 3)) * scale                                   # :103
-    idx, band = rel_band(t, hp.window)
+    idx, band = rel_band(t, hp.window, x.device)
     wk, wv = sd[f"{p}.weight_K"][0], sd[f"{p}.weight_V"][0]                    # [2w+1, d]
     qr = q @ wk.t()                                                             # [B,H,T,2w+1]
     rel_k = torch.gather(qr, 3, idx.expand(b, hds, t, t)) * band               # :106-108
@@ -243,7 +264,7 @@ def rpr_attention(sd, p, x, attn_mask, hp, training=False):
     out = align @ v                                                             # :121
     # :123-126  out[i] += sum_{|j-i|<=w} align[i,j] * wV[j-i+w]
     band_p = align * band
-    rel_w = torch.zeros(b, hds, t, 2 * hp.window + 1, dtype=x.dtype)
+    rel_w = torch.zeros(b, hds, t, 2 * hp.window + 1, dtype=band_p.dtype, device=x.device)
     rel_w.scatter_add_(3, idx.expand(b, hds, t, t), band_p)
     out = out + rel_w @ wv
     out = out.transpose(2, 3).reshape(b, c, t)                                  # :128
@@ -325,8 +346,9 @@ def glow_forward(sd, hp, tokens, token_lengths, mels, mel_lengths, speakers=None
     amask = (tmask.unsqueeze(-1) * mmask.unsqueeze(2)).squeeze(1)                               # :102-103
     with torch.no_grad():
         logp = log_prior(z, mean, log_std)
-        path = _mas.maximum_path_numpy(logp.numpy(), amask.numpy(), core=mas_core)              # :116
-        attn = torch.from_numpy(path).to(logp.dtype)
+        # the reference's wrapper leaves the device here (monotonic_align/__init__.py:14-21): D2H, C loop, H2D
+        path = _mas.maximum_path_numpy(logp.float().cpu().numpy(), amask.float().cpu().numpy(), core=mas_core)   # :116
+        attn = torch.from_numpy(path).to(device=logp.device, dtype=mean.dtype)
     mel_mean = mean @ attn                                                                      # :120
     mel_log_std = log_std @ attn                                                                # :121
     logw_target = torch.log(attn.unsqueeze(1).sum(-1) + 1e-7) * tmask                           # :122

@@ -135,3 +135,50 @@ def test_train_steps_radam_noam(case):
     flat = torch.cat([leaves[k].detach().flatten() for k in keys])
     want = g["train_param_digest"]
     assert abs(float(flat.double().norm()) - want[0]) < 1e-4 * want[0]
+
+
+# --------------------------------------------------------------------------- larger cases / data-dependent init
+LARGE = {"vanilla_large": ("Vanilla", [202, 160, 131, 99, 85, 66, 40, 19], [1000, 946, 812, 640, 518, 402, 256, 104], 31, 1234),
+         "se_large": ("SE", [130, 100, 64, 55, 47, 33, 21, 12], [800, 620, 404, 350, 280, 222, 140, 50], 32, 4321)}
+DDI = {"ddi_vanilla": ("Vanilla", [40, 31, 18, 25], [300, 222, 96, 164], 41, 1234),
+       "ddi_se": ("SE", [33, 21], [200, 128], 42, 4321)}
+
+
+@pytest.mark.parametrize("name", list(LARGE))
+def test_full_forward_at_baseline_sizes(name):
+    """B = 8, T_mel up to 1000, T_text up to 202 (BASELINE.json configs[1] / [2] shapes): the oracle's forward,
+    alignment and losses against the reference-made fixture (big tensors are stored every 8th frame + a digest)."""
+    mode, tls, mls, bseed, wseed = LARGE[name]
+    g = np.load(os.path.join(GOLD, "model_%s.npz" % name))
+    sd = _state_dict(mode, wseed)
+    assert checksum(torch.cat([sd[k].flatten() for k in sorted(sd)]).numpy()) == str(g["weights_sha"])
+    hp = O.OracleHP(mode=mode)
+    tokens, tl, mels, ml, spk = synth_batch(bseed, tls, mls)
+    stride = int(g["stride"])
+    with torch.no_grad():
+        out = O.glow_forward(sd, hp, tokens, tl, mels, ml, spk)
+    assert np.array_equal(out[6].argmax(1).numpy().astype(np.int16), g["fw_attn_pos"])
+    for got, key in zip(out[:3], ["fw_z", "fw_mel_mean", "fw_mel_log_std"]):
+        assert rel_err(got[..., ::stride], g[key]) < TOL, key
+        d = _digest(got, 13)
+        assert abs(d[0] - g[key + "_digest"][0]) < TOL * g[key + "_digest"][0], key
+    for got, key in zip(out[3:6], ["fw_logdet", "fw_logw", "fw_logw_target"]):
+        assert rel_err(got, g[key]) < TOL, key
+    total, mle, mse = O.losses(out, ml, hp)
+    assert abs(float(mle) - g["fw_losses"][0]) < 1e-4 * abs(g["fw_losses"][0])
+    assert abs(float(mse) - g["fw_losses"][1]) < 1e-4 * abs(g["fw_losses"][1])
+
+
+@pytest.mark.parametrize("name", list(DDI))
+def test_actnorm_data_dependent_init(name):
+    """Activation_Norm.initialize (Modules.py:698-711) through all 12 blocks: logs / bias of every block and the
+    resulting z / logdet against the reference run on an uninitialised model."""
+    mode, tls, mls, bseed, wseed = DDI[name]
+    g = np.load(os.path.join(GOLD, "model_%s.npz" % name))
+    sd = _state_dict(mode, wseed)
+    hp = O.OracleHP(mode=mode)
+    tokens, tl, mels, ml, spk = synth_batch(bseed, tls, mls)
+    emb = sd["layer_Dict.LUT.weight"][spk] if hp.se else None
+    z, ld, logs, bias = O.decoder_ddi(sd, mels, O.length_mask(ml), hp, emb)
+    assert rel_err(logs, g["logs"]) < 1e-3 and rel_err(bias, g["bias"]) < 1e-3
+    assert rel_err(z, g["z"]) < 1e-3 and rel_err(ld, g["logdet"]) < 1e-3

@@ -25,6 +25,11 @@ def _events(torch):
 
 
 def run_mas(args, bench):
+    bench.emit_json(mas_line(args, bench))
+    return 0
+
+
+def mas_line(args, bench):
     import numpy as np
     import torch
     from glow_tts_b200 import _lib
@@ -131,12 +136,15 @@ def run_mas(args, bench):
                          "paths_equal_gpu": same},
         "grid": grid,
     }
-    import bench
-    bench.emit_json(line)
-    return 0
+    return line
 
 
 def run_decoder(args, bench):
+    bench.emit_json(decoder_line(args, bench))
+    return 0
+
+
+def decoder_line(args, bench):
     import torch
     from glow_tts_b200 import _lib
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -192,9 +200,7 @@ def run_decoder(args, bench):
                                  "frac": gbs / pk["hbm_gbs"], "note": "algorithmic 1920*s B per mel frame (SURVEY 8d)"},
         "sweep": sweep,
     }
-    import bench
-    bench.emit_json(line)
-    return 0
+    return line
 
 
 def run_inference(args, bench):

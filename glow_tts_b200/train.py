@@ -444,7 +444,15 @@ class GraphedTrainStep:
             with torch.cuda.graph(graph, pool=self._pool, stream=cap):
                 loss = self.step.run(bk._dev_batch, device_schedule=True, geometry=bk.geo)
         bk.keep.extend(keep)
+        # the graph's result tensors are placeholders until its first replay: give them the eager step's results
+        eager_loss, eager_last = bk.loss, bk.last
         bk.graph, bk.loss, bk.last = graph, loss, dict(self.step.last)
+        with torch.no_grad():
+            if eager_loss is not None:
+                bk.loss.copy_(eager_loss)
+            for k, v in eager_last.items():
+                if k in bk.last and bk.last[k] is not v:
+                    bk.last[k].copy_(v)
         bk.launches = _lib.launch_count() - n0                  # libglowcore kernels inside the graph
 
     def run(self, batch_host=None, global_frames=None, global_positions=None):

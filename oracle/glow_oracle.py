@@ -135,7 +135,7 @@ def inv1x1(x, mask, weight, reverse=False, split=4):
     grouped = x[:, idx.reshape(-1)].view(b, split, c // split, t)
     mixed = torch.einsum("ok,bkgt->bogt", w, grouped)
     z = torch.zeros_like(x)
-    z[:, idx.reshape(-1)] = mixed.reshape(b, c, t)
+    z[:, idx.reshape(-1)] = mixed.reshape(b, c, t).to(z.dtype)
     z = z * mask
     if reverse:
         return z, None

@@ -41,9 +41,12 @@ TOL = {
     "fp32-tc": dict(z=1e-3, mel_mean=1e-3, mel_log_std=1e-3, logdet=1e-3, logw=1e-3, logw_target=1e-3, mle=1e-3, mse=1e-3,
                     mas_diff=0.0, grad_norm=3e-3, grad_total=3e-3, train_mle=2e-3, train_mse=2e-3, train_gn=5e-3, train_param_norm=1e-4),
     # bf16: z / logdet carry 12 blocks x 10 GEMMs of bf16 rounding; mel_mean / mel_log_std / logw_target differ where
-    # the alignment differs (mas_diff = fraction of real mel frames whose token differs from the reference path)
-    "bf16": dict(z=5e-2, mel_mean=None, mel_log_std=None, logdet=2e-2, logw=3e-2, logw_target=None, mle=1e-2, mse=1e-1,
-                 mas_diff=0.05, grad_norm=1e-1, grad_total=5e-2, train_mle=2e-2, train_mse=1e-1, train_gn=1e-1, train_param_norm=1e-3),
+    # the alignment differs (mas_diff = fraction of real mel frames whose token differs from the reference path) and
+    # are only recorded.  Measured on B200 (profiles/parity_r02a_large.json; vanilla / SE): z 6.9e-3 / 1.5e-2, logdet
+    # 2.2e-4 / 6.9e-5, MLE 3.7e-3 / 6.8e-3, mas_diff 2.1e-4 / 1.2e-2, whole-gradient norm 5.3e-3 / 2.8e-2, worst single
+    # parameter's gradient digest 6.4e-2 / 1.8e-1 (small tensors: ActNorm bias, biases behind a ReLU).
+    "bf16": dict(z=3e-2, mel_mean=None, mel_log_std=None, logdet=2e-3, logw=2e-2, logw_target=None, mle=1.5e-2, mse=5e-2,
+                 mas_diff=0.03, grad_norm=3e-1, grad_total=6e-2, train_mle=2e-2, train_mse=6e-2, train_gn=6e-2, train_param_norm=1e-6),
 }
 MEASURED = {}
 

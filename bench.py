@@ -680,7 +680,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "mas", "decoder", "inference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32-tc"])
     ap.add_argument("--mode", default="Vanilla", choices=["Vanilla", "SE"], help="Vanilla: configs[1]; SE: configs[2] (SE-LUT)")
     ap.add_argument("--kind", default=None, choices=["lj", "ljvctk"], help="batch shapes (default: lj for Vanilla, ljvctk for SE)")
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default 32; 8 for --mode SE)")

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libglowcore.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "glowcore.h")
 
-GLOW_F32, GLOW_I32, GLOW_BF16, GLOW_BF16_SIMT = 0, 1, 2, 3
+GLOW_F32, GLOW_I32, GLOW_BF16, GLOW_BF16_SIMT, GLOW_F32_TC = 0, 1, 2, 3, 4
 
 _c = ctypes
 _P, _I, _F, _Z, _U64, _U32 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_uint64, _c.c_uint32
@@ -74,6 +74,8 @@ SIGNATURES = {
     "glow_flow_param_slots": (_I, [_PCFG]),
     "glow_flow_wpack_floats": (_Z, [_PCFG]),
     "glow_flow_wpack_tc_elems": (_Z, [_PCFG]),
+    "glow_flow_wpack_tc_elems_for": (_Z, [_PCFG, _I]),
+    "glow_flow_wait_block_grads": (_I, [_P, _I]),
     "glow_flow_workspace_elems": (_I, [_PCFG, _I, _I, _I, ctypes.POINTER(_Z)]),
     "glow_flow_prepare": (_I, [_PCFG, _P, _P, _I, _P, _P, _P]),
     "glow_flow_forward": (_I, [_PCALL, _P, _P, _P]),
@@ -84,6 +86,7 @@ SIGNATURES = {
     "glow_flow_backward": (_I, [_PCALL, _P, _P, _P, _P, _P]),
     "glow_flow_backward_params": (_I, [_PCALL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_flow_param_grads": (_I, [_PCFG, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "glow_conv_wgrad": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _c.c_longlong, _I, _I, _P]),
     "glow_rpr_attention_forward": (_I, [_PATTN, _P, _P, _P]),
     "glow_rpr_attention_backward": (_I, [_PATTN, _P, _P, _P, _P, _P, _P, _P, _P]),
     "glow_rows_conv_slab_elems": (_Z, [_I, _I, _I]),

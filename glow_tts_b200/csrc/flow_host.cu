@@ -32,8 +32,9 @@ static int check_call(const glow_flow_call *call, bool need_bwd)
     GLOW_REQUIRE(call != nullptr, GLOW_ERR_INVALID, "flow: null call");
     int rc = check_cfg(&call->cfg);
     if (rc) return rc;
-    GLOW_REQUIRE(call->precision == GLOW_F32 || call->precision == GLOW_BF16 || call->precision == GLOW_BF16_SIMT,
-                 GLOW_ERR_INVALID, "flow: precision must be GLOW_F32, GLOW_BF16 or GLOW_BF16_SIMT");
+    GLOW_REQUIRE(call->precision == GLOW_F32 || call->precision == GLOW_BF16 || call->precision == GLOW_BF16_SIMT ||
+                     call->precision == GLOW_F32_TC,
+                 GLOW_ERR_INVALID, "flow: precision must be GLOW_F32, GLOW_BF16, GLOW_BF16_SIMT or GLOW_F32_TC");
     GLOW_REQUIRE(call->batch >= 1 && call->t_max >= 2, GLOW_ERR_INVALID, "flow: batch=%d t_max=%d", call->batch,
                  call->t_max);
     GLOW_REQUIRE(call->rows_pad > 0 && call->rows_pad % kRowTile == 0, GLOW_ERR_INVALID,
@@ -58,7 +59,7 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
     c.wpack = call->wpack;
     c.wpack_tc = (const __nv_bfloat16 *)call->wpack_tc;
     c.bp = make_block_pack(call->cfg.spk_dim);
-    c.bt = make_block_pack_tc();
+    c.bt = make_block_pack_tc(call->precision == GLOW_F32_TC ? 3 : 1);
     c.wl = make_work_layout(call->cfg.blocks, (size_t)call->rows_pad, call->batch, call->training != 0);
     c.ws_f32 = call->ws_f32;
     c.ws_act = (ActT *)call->ws_act;
@@ -75,13 +76,13 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
 // Build the per-tensor job table from the flat parameter buffer + host offset table.
 static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *off, float *grads,
                        float *wpack, __nv_bfloat16 *wpack_tc, const float *dwpack, WnJobs *jobs, SmallJobs *small,
-                       bool tc_only = false, int k0 = 0, int k1 = -1)
+                       bool tc_only = false, int k0 = 0, int k1 = -1, bool split = false)
 {
     if (k1 < 0) k1 = cfg.blocks;
     const bool se = cfg.spk_dim > 0;
     const int per_block = slots_per_block(se);
     const BlockPack bp = make_block_pack(cfg.spk_dim);
-    const BlockPackTC bt = make_block_pack_tc();
+    const BlockPackTC bt = make_block_pack_tc(split ? 3 : 1);
     jobs->count = 0;
     int cta = 0;
     small->blocks = k1 - k0;
@@ -108,6 +109,11 @@ static void build_jobs(const FlowCfg &cfg, const float *params, const int64_t *o
         j.bn_wt = has_tc ? slice_of(k_in) : k_in;
         j.cta_begin = cta;
         j.skip_f32 = (tc_only && has_tc) ? 1 : 0;
+        j.split = (split && has_tc) ? 1 : 0;
+        // logical A panels of the GEMMs that read the images (flow_tc.cuh TcSplitOps): the forward GEMM's K = k_in is one
+        // panel; the data-gradient GEMM's K = n_out is one panel except b_rs (two of 192: d res | d skip) and b_in (of 96)
+        j.kp_w = k_in / 8;
+        j.kp_wt = (taps > 1 ? kBInPanelCols : (n_out > kH ? kH : n_out)) / 8;
         cta += n_out / 8;
     };
     for (int k = k0; k < k1; ++k) {
@@ -181,6 +187,13 @@ size_t glow_flow_wpack_tc_elems(const glow_flow_config *cfg)
     return make_block_pack_tc().total * (size_t)cfg->blocks;
 }
 
+size_t glow_flow_wpack_tc_elems_for(const glow_flow_config *cfg, int precision)
+{
+    if (check_cfg(cfg)) return 0;
+    if (precision == GLOW_F32) return 0;
+    return make_block_pack_tc(precision == GLOW_F32_TC ? 3 : 1).total * (size_t)cfg->blocks;
+}
+
 int glow_flow_workspace_elems(const glow_flow_config *cfg, int rows_pad, int batch, int training, size_t out[4])
 {
     int rc = check_cfg(cfg);
@@ -198,13 +211,14 @@ int glow_flow_prepare(const glow_flow_config *cfg, const float *params, const in
     int rc = check_cfg(cfg);
     if (rc) return rc;
     GLOW_REQUIRE(params && offsets_host && wpack, GLOW_ERR_INVALID, "flow_prepare: null pointer");
-    GLOW_REQUIRE(precision == GLOW_F32 || ((precision == GLOW_BF16 || precision == GLOW_BF16_SIMT) && wpack_tc),
+    GLOW_REQUIRE(precision == GLOW_F32 ||
+                     ((precision == GLOW_BF16 || precision == GLOW_BF16_SIMT || precision == GLOW_F32_TC) && wpack_tc),
                  GLOW_ERR_INVALID, "flow_prepare: bad precision / missing wpack_tc");
     const FlowCfg fc = to_cfg(cfg);
     static thread_local WnJobs jobs;
     SmallJobs small{};
     build_jobs(fc, params, offsets_host, nullptr, wpack, precision != GLOW_F32 ? (__nv_bfloat16 *)wpack_tc : nullptr,
-               nullptr, &jobs, &small, precision == GLOW_BF16);
+               nullptr, &jobs, &small, precision == GLOW_BF16 || precision == GLOW_F32_TC, 0, -1, precision == GLOW_F32_TC);
     const BlockPack bp = make_block_pack(cfg->spk_dim);
     rc = launch_block_small(small, wpack, bp.total, bp, (cudaStream_t)stream);
     if (rc) return rc;
@@ -236,7 +250,18 @@ int glow_flow_forward(const glow_flow_call *call, const float *mel, float *z, fl
     if (rc) return rc;
     GLOW_REQUIRE(mel && z && logdet, GLOW_ERR_INVALID, "flow_forward: null pointer");
     if (call->precision == GLOW_F32) return flow_forward_f32(make_ctx<float>(call), mel, call->t_max, z, logdet);
+    if (call->precision == GLOW_F32_TC) return flow_forward_f32tc(make_ctx<float>(call), mel, call->t_max, z, logdet);
     return flow_forward_bf16(make_ctx<__nv_bfloat16>(call), mel, call->t_max, z, logdet, call->precision == GLOW_BF16);
+}
+
+int glow_flow_wait_block_grads(glow_stream_t stream, int block)
+{
+    GLOW_REQUIRE(block >= 0 && block < kMaxBlocks, GLOW_ERR_INVALID, "flow_wait_block_grads: block=%d", block);
+    SideStream *ss = nullptr;
+    int rc = side_stream(&ss);
+    if (rc) return rc;
+    GLOW_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->pg_done[block], 0));
+    return GLOW_OK;
 }
 
 int glow_flow_pack_rows(const glow_flow_call *call, const float *mel, float *x_rows)
@@ -266,6 +291,7 @@ int glow_flow_block_forward(const glow_flow_call *call, int block, const float *
                  call->cfg.blocks);
     GLOW_REQUIRE(!call->training, GLOW_ERR_INVALID, "flow_block_forward: uses the inference workspace (training = 0)");
     if (call->precision == GLOW_F32) return flow_block_forward_f32(make_ctx<float>(call), block, x_rows, z_rows);
+    if (call->precision == GLOW_F32_TC) return flow_block_forward_f32tc(make_ctx<float>(call), block, x_rows, z_rows);
     return flow_block_forward_bf16(make_ctx<__nv_bfloat16>(call), block, x_rows, z_rows, call->precision == GLOW_BF16);
 }
 
@@ -275,6 +301,7 @@ int glow_flow_reverse(const glow_flow_call *call, const float *z, float *mel, fl
     if (rc) return rc;
     GLOW_REQUIRE(mel && z, GLOW_ERR_INVALID, "flow_reverse: null pointer");
     if (call->precision == GLOW_F32) return flow_reverse_f32(make_ctx<float>(call), z, call->t_max, mel, fill);
+    if (call->precision == GLOW_F32_TC) return flow_reverse_f32tc(make_ctx<float>(call), z, call->t_max, mel, fill);
     return flow_reverse_bf16(make_ctx<__nv_bfloat16>(call), z, call->t_max, mel, fill, call->precision == GLOW_BF16);
 }
 
@@ -290,6 +317,8 @@ int glow_flow_backward(const glow_flow_call *call, const float *dz, const float 
                                         (cudaStream_t)call->stream));
     if (call->precision == GLOW_F32)
         return flow_backward_f32(make_ctx<float>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk);
+    if (call->precision == GLOW_F32_TC)
+        return flow_backward_f32tc(make_ctx<float>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk);
     return flow_backward_bf16(make_ctx<__nv_bfloat16>(call), dz, call->t_max, dlogdet, dwpack, dmel, dspk,
                               call->precision == GLOW_BF16);
 }
@@ -305,9 +334,10 @@ int glow_flow_backward_params(const glow_flow_call *call, const float *dz, const
     if (dspk)
         GLOW_CHECK_CUDA(cudaMemsetAsync(dspk, 0, sizeof(float) * call->batch * call->cfg.spk_dim,
                                         (cudaStream_t)call->stream));
-    if (call->precision == GLOW_F32) {
+    if (call->precision == GLOW_F32 || call->precision == GLOW_F32_TC) {
         FlowCtx<float> c = make_ctx<float>(call);
         c.pg_params = params; c.pg_offsets = offsets_host; c.pg_grads = grads;
+        if (call->precision == GLOW_F32_TC) return flow_backward_f32tc(c, dz, call->t_max, dlogdet, dwpack, dmel, dspk);
         return flow_backward_f32(c, dz, call->t_max, dlogdet, dwpack, dmel, dspk);
     }
     FlowCtx<__nv_bfloat16> c = make_ctx<__nv_bfloat16>(call);

@@ -44,6 +44,7 @@ constexpr int kBnH = GLOW_BN_H;         // N = 192
 constexpr int kBnEnd = GLOW_BN_END;     // N = 160 (End: interleaved mean, logs)
 constexpr int kBnHalf = kCh;            // N = 80
 constexpr int kTcKs = GLOW_TC_KS;       // K per weight stage for the K = 192 panels
+constexpr int kBInPanelCols = 96;       // K per A panel of the k = 5 data-gradient GEMM (flow_tc.cuh kBInPanel)
 
 struct FlowCfg {               // == glow_flow_config (include/glowcore.h)
     int blocks, channels, hidden, layers, kernel, split, spk_dim;
@@ -106,11 +107,12 @@ struct BlockPackTC {           // element offsets (bf16) inside one block's bf16
     size_t end_w, end_wt;
     size_t total;
 };
-inline BlockPackTC make_block_pack_tc()
+// mult = 3: the split images of GLOW_F32_TC (per logical A panel: W_hi, W_hi, W_lo -- flow_tc.cuh AMODE 2)
+inline BlockPackTC make_block_pack_tc(int mult = 1)
 {
     BlockPackTC p{};
     size_t o = 0;
-    auto take = [&](size_t n) { size_t r = o; o += (n + 63) & ~(size_t)63; return r; };
+    auto take = [&](size_t n) { size_t r = o; o += (n * (size_t)mult + 63) & ~(size_t)63; return r; };
     p.start_w = take((size_t)kCh * kH); p.start_wt = take((size_t)kH * kCh);
     for (int i = 0; i < kLayers; ++i) {
         const int rs_n = (i < kLayers - 1) ? kG : kH;

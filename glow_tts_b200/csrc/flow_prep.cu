@@ -47,6 +47,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return *reinterpret_cast<const uint32_t *>(&t);
 }
 
+// bf16 pair of what the bf16 rounding of (a, b) lost (the "lo" part of the GLOW_F32_TC operand split)
+__device__ __forceinline__ uint32_t split_lo(float a, float b)
+{
+    return pack_bf16x2(a - __bfloat162float(__float2bfloat16_rn(a)), b - __bfloat162float(__float2bfloat16_rn(b)));
+}
+
 constexpr int kWnGroup = 8;                    // packed channels per CTA
 constexpr int kWnMaxPer = kTaps * kH;          // 960 = the k=5 gate conv; every other tensor is smaller
 constexpr int kWnThreads = 256;
@@ -63,6 +69,7 @@ wn_pack_kernel(const __grid_constant__ WnJobs jobs)
     __nv_bfloat16 *__restrict__ slabW = J.slabW, *__restrict__ slabWT = J.slabWT;
     const int n_out = J.n_out, k_in = J.k_in, taps = J.taps, interleave = J.interleave;
     const int bn_w = J.bn_w, bn_wt = J.bn_wt;
+    const int split = J.split, kp_w = J.kp_w, kp_wt = J.kp_wt;
     const int grp = blockIdx.x - J.cta_begin, np0 = grp * kWnGroup, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int per = k_in * taps, pitch = per + 1;
@@ -109,8 +116,19 @@ wn_pack_kernel(const __grid_constant__ WnJobs jobs)
             uint4 q;
             q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
             q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
-            *reinterpret_cast<uint4 *>(slabWT + ((((size_t)(k / bn_wt) * taps + tap) * (n_out / 8) + grp) * bn_wt
-                                                 + k % bn_wt) * 8) = q;
+            if (!split) {
+                *reinterpret_cast<uint4 *>(slabWT + ((((size_t)(k / bn_wt) * taps + tap) * (n_out / 8) + grp) * bn_wt
+                                                     + k % bn_wt) * 8) = q;
+            } else {        // K chunk grp of logical panel grp / kp_wt -> virtual panels 3p (hi), 3p + 1 (hi), 3p + 2 (lo)
+                uint4 lo;
+                lo.x = split_lo(w[0], w[1]); lo.y = split_lo(w[2], w[3]); lo.z = split_lo(w[4], w[5]); lo.w = split_lo(w[6], w[7]);
+                const int pl = grp / kp_wt, cc = grp % kp_wt;
+                const size_t base = ((size_t)(k / bn_wt) * taps + tap) * (size_t)(3 * (n_out / 8));
+#pragma unroll
+                for (int sp = 0; sp < 3; ++sp)
+                    *reinterpret_cast<uint4 *>(slabWT + ((base + (size_t)(3 * pl + sp) * kp_wt + cc) * bn_wt + k % bn_wt) * 8) =
+                        sp == 2 ? lo : q;
+            }
         }
     }
     // (tap, k/8, channel) items, channel fastest: 8 consecutive k of one channel
@@ -131,7 +149,18 @@ wn_pack_kernel(const __grid_constant__ WnJobs jobs)
             uint4 q;
             q.x = pack_bf16x2(w[0], w[1]); q.y = pack_bf16x2(w[2], w[3]);
             q.z = pack_bf16x2(w[4], w[5]); q.w = pack_bf16x2(w[6], w[7]);
-            *reinterpret_cast<uint4 *>(slabW + ((((size_t)(np / bn_w) * taps + tap) * k8n + k8) * bn_w + np % bn_w) * 8) = q;
+            if (!split) {
+                *reinterpret_cast<uint4 *>(slabW + ((((size_t)(np / bn_w) * taps + tap) * k8n + k8) * bn_w + np % bn_w) * 8) = q;
+            } else {
+                uint4 lo;
+                lo.x = split_lo(w[0], w[1]); lo.y = split_lo(w[2], w[3]); lo.z = split_lo(w[4], w[5]); lo.w = split_lo(w[6], w[7]);
+                const int pl = k8 / kp_w, cc = k8 % kp_w;
+                const size_t base = ((size_t)(np / bn_w) * taps + tap) * (size_t)(3 * k8n);
+#pragma unroll
+                for (int sp = 0; sp < 3; ++sp)
+                    *reinterpret_cast<uint4 *>(slabW + ((base + (size_t)(3 * pl + sp) * kp_w + cc) * bn_w + np % bn_w) * 8) =
+                        sp == 2 ? lo : q;
+            }
         }
     }
 }

@@ -3,6 +3,8 @@
 // Templated on the activation type and on an `Ops` policy that provides the
 // GEMM-shaped steps (SimtOps: fp32 CUDA cores; TcOps: bf16 tcgen05).
 #pragma once
+#include <stdlib.h>
+
 #include "flow_elem.cuh"
 #include "flow_simt.cuh"
 
@@ -55,6 +57,7 @@ inline const float *spkb_ptr(const FlowCtx<ActT> &c, int k, int i)
 template <typename ActT, bool FAST>
 struct SimtOps {
     using Ctx = FlowCtx<ActT>;
+    static constexpr bool kOwnWgrad = false;     // weight gradients on the library GEMM: the cross-check of wgrad_tc
     static const float *wp(const Ctx &c, int k) { return c.wpack + (size_t)k * c.bp.total; }
 
     static int start(const Ctx &c, int k, const Bufs<ActT> &b)
@@ -298,17 +301,38 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         const int wm = kBf16 ? 1 : 0;
         auto fork = [&]() -> int {
             GLOW_CHECK_CUDA(cudaEventRecord(ss->fork[set], c.st));
-            GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->fork[set], 0));
+            for (int l = 0; l < kWgLanes; ++l) GLOW_CHECK_CUDA(cudaStreamWaitEvent(ss->lane[l], ss->fork[set], 0));
             return GLOW_OK;
         };
+
         GLOW_TRY(fork());                                  // DOUTS, DOUT are final
+        // Weight gradients: on the tcgen05 paths our own kernel (wgrad_tc.cuh), one launch per shape class and block,
+        // issued when the block's last operand exists (below, after the last b_in): three kernels of 2 - 24 CTAs that
+        // walk the whole row axis while the NEXT block's data-gradient chain runs.  The CUDA-core modes keep the
+        // library GEMM, forked per producer, which makes them an independent check of wgrad_tc
+        // (tests/test_flow_gpu.py compares the two paths).
+        static const bool lib_wgrad = getenv("GLOW_WGRAD_CUBLAS") != nullptr;
+        const bool own = Ops::kOwnWgrad && !lib_wgrad;
+        WgJobDesc j5[kLayers], j1[2 * kLayers + 1], js[1];
+        int n5 = 0, n1 = 0, ns = 0;
+        // C[taps][K][N] (ldc) = sum_r A[r + tap - 2]^T D[r]
+        auto wg = [&](const void *A, int lda, int K, const void *D, int ldd, int N, float *C, int ldc, int taps) -> int {
+            if (own) {
+                const WgJobDesc d{A, lda, K, D, ldd, N, C, ldc, (long long)K * ldc, false};
+                if (taps > 1) j5[n5++] = d; else if (K == kH) j1[n1++] = d; else js[ns++] = d;
+                return GLOW_OK;
+            }
+            if (taps > 1)    // rows restricted to [2, R-2): A[r + tap - 2] stays inside the buffer
+                return wgrad_gemm(side, wm, A, lda, (const ActT *)D + (size_t)G2 * ldd, ldd, Rw, K, N, C, ldc, taps, lda,
+                                  (long long)K * ldc, 0.f, true, true);
+            return wgrad_gemm(side, wm, A, lda, D, ldd, R, K, N, C, ldc, 1, 0, 0, 0.f, true, true);
+        };
         // dW_end[192][160] = OUT^T DOUTS
-        GLOW_TRY(wgrad_gemm(side, wm, b.OUT, kH, DOUTS, kC, R, kH, kC, dwp + c.bp.end_w, kC, 1, 0, 0, 0.f, true, true));
+        GLOW_TRY(wg(b.OUT, kH, kH, DOUTS, kC, kC, dwp + c.bp.end_w, kC, 1));
         // dW_rs[192][rs_n], skip columns (d(out)); the last layer has only those
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
-            GLOW_TRY(wgrad_gemm(side, wm, b.ACTS[i], kH, DOUT, kH, R, kH, kH, dwp + c.bp.rs_w[i] + (last ? 0 : kH), last ? kH : kG,
-                                1, 0, 0, 0.f, true, true));
+            GLOW_TRY(wg(b.ACTS[i], kH, kH, DOUT, kH, kH, dwp + c.bp.rs_w[i] + (last ? 0 : kH), last ? kH : kG, 1));
         }
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
@@ -325,17 +349,22 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
                 GLOW_CHECK_LAUNCH("spk_bwd_kernel");
             }
             GLOW_TRY(Ops::b_in(c, k, i, DPRE[i], DHnext, DH[i]));
-            GLOW_TRY(fork());                              // DPRE[i], DH[i] are final
-            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row] ; rows restricted to [2, R-2)
-            GLOW_TRY(wgrad_gemm(side, wm, b.H[i], kH, DPRE[i] + (size_t)G2 * kG, kG, Rw, kH, kG, dwp + c.bp.in_w[i], kG,
-                                kTaps, kH, (long long)kH * kG, 0.f, true, true));
+            if (!own || i == 0) GLOW_TRY(fork());          // DPRE[i], DH[i] are final
+            // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row]
+            GLOW_TRY(wg(b.H[i], kH, kH, DPRE[i], kG, kG, dwp + c.bp.in_w[i], kG, kTaps));
             if (i > 0) {        // res columns of the layer below from d(h_i)
-                GLOW_TRY(wgrad_gemm(side, wm, b.ACTS[i - 1], kH, DH[i], kH, R, kH, kH, dwp + c.bp.rs_w[i - 1], kG, 1, 0, 0, 0.f, true, true));
-            } else if (kBf16) {
-                GLOW_TRY(wgrad_gemm(side, 1, b.YA, kCh, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
+                GLOW_TRY(wg(b.ACTS[i - 1], kH, kH, DH[i], kH, kH, dwp + c.bp.rs_w[i - 1], kG, 1));
+            } else if (kBf16 || own) {
+                GLOW_TRY(wg(b.YA, kCh, kCh, DH[0], kH, kH, dwp + c.bp.start_w, kH, 1));
             } else {
                 GLOW_TRY(wgrad_gemm(side, 0, b.Y, kC, DH[0], kH, R, kCh, kH, dwp + c.bp.start_w, kH, 1, 0, 0, 0.f, true, true));
             }
+        }
+        if (own) {              // the block's three batches, side by side on the lanes
+            constexpr bool f32 = !kBf16;
+            GLOW_TRY(wgrad_tc_batch(ss->lane[0], j5, n5, f32, f32, nullptr, R, kTaps, 0, "wgrad_in"));
+            GLOW_TRY(wgrad_tc_batch(ss->lane[1], j1, n1, f32, f32, nullptr, R, 1, 0, "wgrad_1x1"));
+            GLOW_TRY(wgrad_tc_batch(ss->lane[2], js, ns, f32, f32, nullptr, R, 1, 0, "wgrad_start"));
         }
         GLOW_TRY(Ops::b_start(c, k, DH[0], DY));
         {   // every bias gradient of the block: column sums of the gradients the GEMMs above read (one launch)
@@ -357,6 +386,10 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             GLOW_CHECK_LAUNCH("colsum_multi_kernel");
             GLOW_CHECK_CUDA(cudaEventRecord(ss->aux_done[set], ss->aux));
         }
+        for (int l = 1; l < kWgLanes; ++l) {               // lanes join lane 0 (== side)
+            GLOW_CHECK_CUDA(cudaEventRecord(ss->lane_done[l], ss->lane[l]));
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->lane_done[l], 0));
+        }
         GLOW_TRY(wgrad_flush(side));                       // the block's split reductions, one launch
         // ---- back on the main stream: 4x4 mix + ActNorm backward -> dz of the previous block
         const bool need_dz = k > 0 || dmel != nullptr;
@@ -370,6 +403,7 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->aux_done[set], 0));
             GLOW_TRY(param_grads_block(c.cfg, c.pg_params, c.pg_offsets, c.wpack, dwpack, dlogdet, c.rows.utt_len, B,
                                        c.pg_grads, k, side));
+            GLOW_CHECK_CUDA(cudaEventRecord(ss->pg_done[k], side));        // -> glow_flow_wait_block_grads
         }
         GLOW_CHECK_CUDA(cudaEventRecord(ss->done[set], side));
     }

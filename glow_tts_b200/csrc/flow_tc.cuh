@@ -34,12 +34,17 @@
 
 namespace glow {
 
+constexpr int kTcMaxPanels = 12;
 struct TcA {                         // A operand: NP panels of KP columns each
-    const void *p[4];                // panel p starts at p[p] (same tensor + KP columns, or another tensor)
+    const void *p[kTcMaxPanels];     // panel p starts at p[p] (same tensor + KP columns, or another tensor)
 };
 // AMODE 0: A is bf16.  AMODE 1: A is fp32, converted to bf16 while it is staged, and rows whose
 // row_utt is < 0 (guard / tail rows) are staged as zeros -- the reference's `x * mask` in front of
 // every encoder conv (Modules.py:554,567,570) folded into the load.
+// AMODE 2 (GLOW_F32_TC, the 1e-3 tensor-core mode): A is fp32 and every LOGICAL panel is staged three times, as
+// hi = bf16(x), lo = bf16(x - hi), hi; glow_flow_prepare lays the weight image out as W_hi, W_hi, W_lo for the same
+// three VIRTUAL panels, so the accumulator receives x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32 -- the product to
+// 2^-16 relative (the dropped lo * lo term) instead of bf16's 2^-8.  NP counts virtual panels (3 per logical one).
 
 constexpr int kTcRows = 128 + 2 * kGuard;   // staged rows per tile
 constexpr int kTcPitch = 133 * 16;          // slab pitch in bytes: 133 rows -> conflict-free 16 B staging stores
@@ -50,7 +55,7 @@ constexpr int kTcFirstThreads = 384;        // the CTA's FIRST panel is staged b
 constexpr int kTcFirstActive = 360;         // = 24*15 = 20*18 = 10*36
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcMaxStages = 8;
-constexpr int kBInPanel = 96;             // K per A panel of the k = 5 data-gradient GEMM (b_in); 192 = the old two-panel form
+constexpr int kBInPanel = kBInPanelCols;  // K per A panel of the k = 5 data-gradient GEMM (b_in); 192 = the old two-panel form
 constexpr int kTcSmemCap = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (barriers are static)
 constexpr int kTcStagingFloats = 32 * 33;   // per epilogue warp: 32 rows x 32 columns, pitch 33 (conflict free)
 
@@ -83,7 +88,7 @@ struct TcCfg {
     static constexpr int kCenter = (TAPS - 1) / 2;
     static_assert(N % BN == 0 && BN % 16 == 0 && BN <= 256, "BN");
     static_assert(KP % 16 == 0 && KP <= 192 && KP % KS == 0 && KS % 16 == 0, "KP / KS");
-    static_assert(NP >= 1 && NP <= 4, "NP");
+    static_assert(NP >= 1 && NP <= kTcMaxPanels, "NP");
     static_assert(TAPS == 1 || TAPS == 3 || TAPS == 5, "TAPS");
     static_assert((TAPS - 1) / 2 <= kGuard, "taps reach beyond the staged guard rows");
     static_assert(LD % 8 == 0 && LD >= KP, "LD");
@@ -111,9 +116,15 @@ struct TcCfg {
 // per-lane scattered shared destinations and 16 B-row TMA boxes both run at about one 16 B row per
 // cycle: profiles/ubench_r01.md.)  Rows outside [0, rows_pad) (first / last tile) read a zero guard
 // row instead: rows 0-1 and the last rows of every packed buffer are guards (flow_layout.cuh).
+__device__ __forceinline__ uint32_t split_lo_bf16x2(float a, float b)
+{
+    const float ra = a - __bfloat162float(__float2bfloat16_rn(a)), rb = b - __bfloat162float(__float2bfloat16_rn(b));
+    return pack_bf16x2(ra, rb);
+}
+
 template <class Cfg, int LD, int AMODE, int ACTIVE>
 __device__ __forceinline__ void stage_panel(const void *base, uint32_t panel_smem, int idx, int row0, int rows_pad,
-                                            const int32_t *__restrict__ row_utt)
+                                            const int32_t *__restrict__ row_utt, int part = 0)
 {
     constexpr int KPCH = Cfg::kKpch;
     constexpr int kStep = ACTIVE / KPCH;
@@ -166,9 +177,14 @@ __device__ __forceinline__ void stage_panel(const void *base, uint32_t panel_sme
             for (int k = 0; k < kBatch; ++k)
                 if (k0 + k < kIters && r0 + (k0 + k) * kStep < kTcRows) {
                     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (u[k] >= 0)
-                        v = make_uint4(pack_bf16x2(t0[k].x, t0[k].y), pack_bf16x2(t0[k].z, t0[k].w),
-                                       pack_bf16x2(t1[k].x, t1[k].y), pack_bf16x2(t1[k].z, t1[k].w));
+                    if (u[k] >= 0) {
+                        if (AMODE == 2 && part == 1)       // what the bf16 rounding of the hi part lost
+                            v = make_uint4(split_lo_bf16x2(t0[k].x, t0[k].y), split_lo_bf16x2(t0[k].z, t0[k].w),
+                                           split_lo_bf16x2(t1[k].x, t1[k].y), split_lo_bf16x2(t1[k].z, t1[k].w));
+                        else
+                            v = make_uint4(pack_bf16x2(t0[k].x, t0[k].y), pack_bf16x2(t0[k].z, t0[k].w),
+                                           pack_bf16x2(t1[k].x, t1[k].y), pack_bf16x2(t1[k].z, t1[k].w));
+                    }
                     st_shared16(dst + (uint32_t)((k0 + k) * kStep * 16), v);
                 }
         }
@@ -221,14 +237,15 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
             for (int p = 0; p < NP; ++p, ++pc) {
                 const uint32_t buf = pc & 1u;
                 const uint32_t dst = smem_u32(smem) + buf * Cfg::kPanelBytes;
+                const int part = (AMODE == 2 && p % 3 == 1) ? 1 : 0;
                 if (pc == 0) {                                         // shared with the epilogue warps (below)
-                    stage_panel<Cfg, LD, AMODE, kTcFirstActive>(a.p[p], dst, tid, row0, rows_pad, row_utt);
+                    stage_panel<Cfg, LD, AMODE, kTcFirstActive>(a.p[p], dst, tid, row0, rows_pad, row_utt, part);
                     fence_proxy_async();                               // generic-proxy writes -> tcgen05.mma reads
                     mbar_arrive(&a_first);
                     continue;
                 }
                 if (pc >= 2) mbar_wait(&a_empty[buf], ((pc >> 1) - 1u) & 1u);
-                stage_panel<Cfg, LD, AMODE, kTcLoadActive>(a.p[p], dst, tid, row0, rows_pad, row_utt);
+                stage_panel<Cfg, LD, AMODE, kTcLoadActive>(a.p[p], dst, tid, row0, rows_pad, row_utt, part);
                 fence_proxy_async();
                 mbar_arrive(&a_full[buf]);
             }
@@ -437,11 +454,12 @@ int gemm_tc3(const TcA &a, const __nv_bfloat16 *Wslab, const int32_t *row_utt, i
 // glow_flow_prepare, so they are compile-time constants shared with flow_prep.cu.
 template <bool FAST>
 struct TcOps {
+    static constexpr bool kOwnWgrad = true;      // weight gradients on wgrad_tc.cuh (no library GEMM on this path)
     using ActT = __nv_bfloat16;
     using Ctx = FlowCtx<ActT>;
     static const float *wp(const Ctx &c, int k) { return c.wpack + (size_t)k * c.bp.total; }
     static const ActT *ws(const Ctx &c, int k) { return c.wpack_tc + (size_t)k * c.bt.total; }
-    static TcA one(const ActT *p) { return TcA{{p, p, p, p}}; }
+    static TcA one(const ActT *p) { return TcA{{p, p, p, p}}; }      // NP = 1: only p[0] is read
 
     static int start(const Ctx &c, int k, const Bufs<ActT> &b)
     {
@@ -515,6 +533,81 @@ struct TcOps {
     {
         EpiBwdStart e{DY};
         return gemm_tc3<kCh, kBnHalf, kH, 1, kH, 1, 0, kTcKs, 0>(one(DH0), ws(c, k) + c.bt.start_wt, c.rows.row_utt,
+                                                              c.rows.rows_pad, e, c.st, "b_start");
+    }
+};
+
+// ------------------------------------------------------- tensor-core ops at fp32-class accuracy --
+// GLOW_F32_TC: fp32 activations, every GEMM as three bf16 tcgen05 MMAs per product (AMODE 2 above), exact tanhf /
+// expf epilogues (FAST = false).  Same instantiations as TcOps with three virtual panels per logical one; the weight
+// images (glow_flow_prepare, split layout) follow the same virtual-panel order.
+struct TcSplitOps {
+    static constexpr bool kOwnWgrad = true;
+    using ActT = float;
+    using Ctx = FlowCtx<ActT>;
+    static const float *wp(const Ctx &c, int k) { return c.wpack + (size_t)k * c.bp.total; }
+    static const __nv_bfloat16 *ws(const Ctx &c, int k) { return c.wpack_tc + (size_t)k * c.bt.total; }
+    static TcA tri(const ActT *p0, const ActT *p1 = nullptr, const ActT *p2 = nullptr, const ActT *p3 = nullptr)
+    {
+        return TcA{{p0, p0, p0, p1, p1, p1, p2, p2, p2, p3, p3, p3}};
+    }
+
+    static int start(const Ctx &c, int k, const Bufs<ActT> &b)
+    {
+        EpiStart<ActT> e{wp(c, k) + c.bp.start_b, b.H[0], c.rows.row_utt};
+        return gemm_tc3<kH, kBnH, kCh, 3, kCh, 1, 0, kCh, 2>(tri(b.YA), ws(c, k) + c.bt.start_w, c.rows.row_utt,
+                                                          c.rows.rows_pad, e, c.st, "start");
+    }
+    static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
+    {
+        const bool last = i == kLayers - 1;
+        EpiGate<ActT, false> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
+                                drop_cfg(c, k, i)};
+        int rc = gemm_tc3<kG, kBnGate, kH, 3, kH, kTaps, +1, kTcKs, 2>(tri(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
+                                                                    c.rows.rows_pad, eg, c.st, "in_gate");
+        if (rc) return rc;
+        EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
+                            c.rows.row_utt, i == 0, last};
+        if (last)
+            return gemm_tc3<kH, kBnH, kH, 3, kH, 1, 0, kTcKs, 2>(tri(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+                                                              c.rows.rows_pad, er, c.st, "res_skip");
+        return gemm_tc3<kG, kBnGate, kH, 3, kH, 1, 0, kTcKs, 2>(tri(b.ACTS[i]), ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+                                                             c.rows.rows_pad, er, c.st, "res_skip");
+    }
+    static int end(const Ctx &c, int k, const Bufs<ActT> &b, const EpiEnd<ActT, false> &e)
+    {
+        return gemm_tc3<kC, kBnEnd, kH, 3, kH, 1, 0, kTcKs, 2>(tri(b.OUT), ws(c, k) + c.bt.end_w, c.rows.row_utt,
+                                                            c.rows.rows_pad, e, c.st, "end");
+    }
+    // backward
+    static int b_end(const Ctx &c, int k, const ActT *DOUTS, ActT *DOUT)
+    {
+        EpiBwdEnd<ActT> e{DOUT, c.rows.row_utt};
+        return gemm_tc3<kH, kBnH, kC, 3, kC, 1, 0, kC / 2, 2>(tri(DOUTS), ws(c, k) + c.bt.end_wt, c.rows.row_utt,
+                                                           c.rows.rows_pad, e, c.st, "b_end");
+    }
+    static int b_rs(const Ctx &c, int k, int i, const Bufs<ActT> &b, const ActT *DHnext, const ActT *DOUT,
+                    ActT *DINS, ActT *DPRE)
+    {
+        EpiBwdGate<ActT> e{b.TS[i], DINS, DPRE, c.rows.row_utt, drop_cfg(c, k, i)};
+        if (i == kLayers - 1)
+            return gemm_tc3<kH, kBnH, kH, 3, kH, 1, 0, kTcKs, 2>(tri(DOUT), ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt,
+                                                              c.rows.rows_pad, e, c.st, "b_rs");
+        return gemm_tc3<kH, kBnH, kH, 6, kH, 1, 0, kTcKs, 2>(tri(DHnext, DOUT), ws(c, k) + c.bt.rs_wt[i], c.rows.row_utt,
+                                                          c.rows.rows_pad, e, c.st, "b_rs");        // d(res) | d(skip)
+    }
+    static int b_in(const Ctx &c, int k, int i, const ActT *DPRE, const ActT *DHnext, ActT *DH)
+    {
+        constexpr int kKp = kBInPanel;
+        EpiBwdIn<ActT> e{DHnext, DH, c.rows.row_utt};
+        return gemm_tc3<kH, kBnH, kKp, 3 * (kG / kKp), kG, kTaps, -1, kTcKs, 2>(tri(DPRE, DPRE + kKp, DPRE + 2 * kKp, DPRE + 3 * kKp),
+                                                                             ws(c, k) + c.bt.in_wt[i], c.rows.row_utt,
+                                                                             c.rows.rows_pad, e, c.st, "b_in");
+    }
+    static int b_start(const Ctx &c, int k, const ActT *DH0, float *DY)
+    {
+        EpiBwdStart e{DY};
+        return gemm_tc3<kCh, kBnHalf, kH, 3, kH, 1, 0, kTcKs, 2>(tri(DH0), ws(c, k) + c.bt.start_wt, c.rows.row_utt,
                                                               c.rows.rows_pad, e, c.st, "b_start");
     }
 };

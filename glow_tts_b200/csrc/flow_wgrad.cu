@@ -44,7 +44,17 @@ int side_stream(SideStream **out)
     if (!g_side_init[dev]) {
         SideStream &s = g_side[dev];
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        s.lane[0] = s.stream;
+        for (int i = 1; i < kWgLanes; ++i) GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.lane[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kWgLanes; ++i) GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.lane_done[i], cudaEventDisableTiming));
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.enc_stream, cudaStreamNonBlocking));
+        s.enc_lane[0] = s.enc_stream;
+        for (int i = 1; i < kWgLanes; ++i) GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.enc_lane[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kWgLanes; ++i) {
+            GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.enc_lane_done[i], cudaEventDisableTiming));
+            s.enc_lane_pending[i] = false;
+        }
+        s.enc_rr = 0;
         GLOW_CHECK_CUDA(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
         GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.aux_fork, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.aux_done[i], cudaEventDisableTiming));
@@ -52,6 +62,7 @@ int side_stream(SideStream **out)
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < kMaxBlocks; ++i) GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.pg_done[i], cudaEventDisableTiming));
         GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.enc_fork, cudaEventDisableTiming));
         GLOW_CHECK_CUDA(cudaEventCreateWithFlags(&s.enc_done, cudaEventDisableTiming));
         s.enc_pending = false;
@@ -119,7 +130,10 @@ static int lane_of(cudaStream_t st)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
-    return (g_side_init[dev] && st == g_side[dev].enc_stream) ? 1 : 0;
+    if (!g_side_init[dev]) return 0;
+    for (int i = 0; i < kWgLanes; ++i)
+        if (st == g_side[dev].enc_lane[i]) return 1;
+    return 0;
 }
 
 static int split_scratch(SplitScratch **out, int lane)

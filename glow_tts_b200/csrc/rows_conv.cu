@@ -147,6 +147,13 @@ static int check_rows(const glow_rows_conv_call *c, int *shape)
     return GLOW_OK;
 }
 
+// weight gradients on our own tcgen05 kernel (wgrad_tc.cuh); GLOW_WGRAD_CUBLAS=1 puts the library GEMM back (A/B runs)
+static bool own_wgrad()
+{
+    static const bool lib = getenv("GLOW_WGRAD_CUBLAS") != nullptr;
+    return !lib;
+}
+
 }  // namespace glow
 
 using namespace glow;
@@ -242,8 +249,12 @@ int glow_rows_conv_backward_weight(const glow_rows_conv_call *c, const float *x,
     GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
     const int center = (c->taps - 1) / 2;
     // dw[tap][cin][cout] = sum_r x[r + tap - center]^T dy[r]  (x, dy already zero on guard rows)
-    rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout, dw,
-                    c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
+    if (own_wgrad())
+        rc = wgrad_tc(side, x, true, c->cin, c->cin, dy, true, c->cout, c->cout, nullptr, c->rows_pad, c->taps, dw, c->cout,
+                      (long long)c->cin * c->cout, false, 0, "enc_wgrad");
+    else
+        rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout, dw,
+                        c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
     if (rc) return rc;
     if (dbias != nullptr) {
         GLOW_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c->cout, side));
@@ -265,18 +276,29 @@ int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *c, const flo
     SideStream *ss = nullptr;
     rc = side_stream(&ss);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)c->stream, side = ss->enc_stream;
+    // our own kernel runs a job on 2-6 CTAs for its whole row range: jobs go round robin over the lanes so that
+    // several run side by side; the library GEMM (GLOW_WGRAD_CUBLAS) keeps its single lane (one handle / scratch)
+    const int ln = own_wgrad() ? (ss->enc_rr++ % kWgLanes) : 0;
+    cudaStream_t st = (cudaStream_t)c->stream, side = ss->enc_lane[ln];
     GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_fork, st));
     GLOW_CHECK_CUDA(cudaStreamWaitEvent(side, ss->enc_fork, 0));
     const int center = (c->taps - 1) / 2;
     if (c->taps == 1) {
         // a 1x1 conv's gradient in torch's [cout][cin][1] layout IS dy^T x: one GEMM that accumulates straight into
         // the gradient buffer (beta = 1) -- no partials, no reduction, no permute-add (25 of the encoder's 41 convs)
-        rc = wgrad_gemm(side, 2, dy, c->cout, x, c->cin, c->rows_pad, c->cout, c->cin, grad_w, c->cin, 1, 0, 0, 1.f);
+        if (own_wgrad())
+            rc = wgrad_tc(side, dy, true, c->cout, c->cout, x, true, c->cin, c->cin, nullptr, c->rows_pad, 1, grad_w, c->cin, 0,
+                          true, 0, "enc_wgrad");
+        else
+            rc = wgrad_gemm(side, 2, dy, c->cout, x, c->cin, c->rows_pad, c->cout, c->cin, grad_w, c->cin, 1, 0, 0, 1.f);
         if (rc) return rc;
     } else {
-        rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout,
-                        scratch, c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
+        if (own_wgrad())
+            rc = wgrad_tc(side, x, true, c->cin, c->cin, dy, true, c->cout, c->cout, nullptr, c->rows_pad, c->taps, scratch, c->cout,
+                          (long long)c->cin * c->cout, false, 0, "enc_wgrad");
+        else
+            rc = wgrad_gemm(side, 2, x, c->cin, dy + (size_t)center * c->cout, c->cout, c->rows_pad - 2 * center, c->cin, c->cout,
+                            scratch, c->cout, c->taps, c->cin, (long long)c->cin * c->cout, 0.f);
         if (rc) return rc;
         GLOW_REQUIRE(c->taps <= kAccTaps && c->cout % 32 == 0 && c->cin % 32 == 0, GLOW_ERR_UNSUPPORTED,
                      "rows_conv_backward_weight_accum: shape %d x %d x %d", c->cout, c->cin, c->taps);
@@ -287,8 +309,8 @@ int glow_rows_conv_backward_weight_accum(const glow_rows_conv_call *c, const flo
         colsum_kernel<float><<<dim3(c->cout / 32, 16), 256, 0, side>>>(dy, c->cout, c->rows_pad, c->cout, grad_b);
         GLOW_CHECK_LAUNCH("colsum_kernel");
     }
-    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_done, side));
-    ss->enc_pending = true;
+    GLOW_CHECK_CUDA(cudaEventRecord(ss->enc_lane_done[ln], side));
+    ss->enc_lane_pending[ln] = true;
     return GLOW_OK;
 }
 
@@ -297,10 +319,11 @@ int glow_side_join(glow_stream_t stream)
     SideStream *ss = nullptr;
     int rc = side_stream(&ss);
     if (rc) return rc;
-    if (ss->enc_pending) {
-        GLOW_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->enc_done, 0));
-        ss->enc_pending = false;
-    }
+    for (int i = 0; i < kWgLanes; ++i)
+        if (ss->enc_lane_pending[i]) {
+            GLOW_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ss->enc_lane_done[i], 0));
+            ss->enc_lane_pending[i] = false;
+        }
     return GLOW_OK;
 }
 

@@ -139,7 +139,9 @@ def precision_tag(precision):
         return _lib.GLOW_BF16, torch.bfloat16
     if precision == "bf16-simt":          # bf16 storage on the CUDA-core GEMM: device cross-check of the tcgen05 path
         return _lib.GLOW_BF16_SIMT, torch.bfloat16
-    raise ValueError("precision must be 'fp32', 'bf16' or 'bf16-simt', got %r" % (precision,))
+    if precision == "fp32-tc":            # fp32 storage, tcgen05 with every operand split into bf16 hi + lo parts
+        return _lib.GLOW_F32_TC, torch.float32
+    raise ValueError("precision must be 'fp32', 'fp32-tc', 'bf16' or 'bf16-simt', got %r" % (precision,))
 
 
 class FlowPlan:
@@ -155,6 +157,7 @@ class FlowPlan:
         self.slots = slots
         self.wpack_floats = L.glow_flow_wpack_floats(ctypes.byref(self.cfg))
         self.wpack_tc_elems = L.glow_flow_wpack_tc_elems(ctypes.byref(self.cfg))
+        self.wpack_tc_elems_for = lambda tag: L.glow_flow_wpack_tc_elems_for(ctypes.byref(self.cfg), tag)
         self._ws = {}
         self._wpack = {}
 
@@ -163,7 +166,7 @@ class FlowPlan:
         key = (str(device), tag)
         if key not in self._wpack:
             wp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
-            wtc = (torch.empty(self.wpack_tc_elems, dtype=torch.bfloat16, device=device)
+            wtc = (torch.empty(self.wpack_tc_elems_for(tag), dtype=torch.bfloat16, device=device)
                    if tag != _lib.GLOW_F32 else None)
             dwp = torch.empty(self.wpack_floats, dtype=torch.float32, device=device)
             self._wpack[key] = (wp, wtc, dwp)
@@ -292,6 +295,7 @@ class FlowDecoderFn(torch.autograd.Function):
                                                           _lib.ptr(dwp), _lib.ptr(dmel), _lib.ptr(dspk), _lib.ptr(flat),
                                                           offs.ctypes.data, _lib.ptr(gflat))
                 _lib.check(rc, "glow_flow_backward_params")
+                owner.fused_backward_calls = getattr(owner, "fused_backward_calls", 0) + 1
                 return (None, None, dmel, dspk, None) + (None,) * ctx.n_params
             rc = _lib.lib().glow_flow_backward(ctypes.byref(call), _lib.ptr(dz), _lib.ptr(dlogdet), _lib.ptr(dwp),
                                                _lib.ptr(dmel), _lib.ptr(dspk))

@@ -518,7 +518,7 @@ class Encoder(torch.nn.Module):
         if self.precision == "bf16" and (host_lengths is not None or token_rows is not None) and self.rows_supported:
             return self._forward_rows(x, mask, speakers, lengths, host_lengths, token_rows)
         # fp32 mode is the parity mode: keep cuDNN from silently using TF32 for the convs
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.precision != "fp32"):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.precision.startswith("fp32")):
             return self._forward(x, mask, speakers, lengths)
 
     @property
@@ -727,7 +727,7 @@ class GlowTTS(torch.nn.Module):
             # The fp32 parity mode keeps the reference's own expression for log_P (a differently ordered sum
             # could flip a near-tie of the search); the rest is exact either way.
             with torch.no_grad():
-                if dec.precision == "fp32":
+                if dec.precision.startswith("fp32"):
                     log_p = self._log_p(z, mean, log_std)
                 else:
                     log_p = _align.log_p(z, mean, log_std, t_len, m_len)

@@ -181,6 +181,50 @@ class TrainStep:
         # device step counter: mixed into the kernels' dropout seeds (see _lib.set_step_counter)
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
         _lib.set_step_counter(device, self.step_counter)
+        # Data parallelism: the flat gradient buffer is all-reduced in BUCKETS -- one per decoder block, issued on a
+        # communication stream as soon as that block's parameter gradients are final (glow_flow_wait_block_grads), so
+        # block k's reduction runs while blocks k-1 .. 0 are still in their backward; the encoder's slice goes last.
+        # GLOW_ALLREDUCE_OVERLAP=0: one all-reduce of the whole buffer after the backward (round 1; fully exposed).
+        self.overlap_allreduce = self.world > 1 and os.environ.get("GLOW_ALLREDUCE_OVERLAP", "1") != "0"
+        self._comm = None
+        self._buckets = None
+
+    def _grad_buckets(self):
+        """[(lo, hi)] element ranges of the flat buffer: decoder blocks (in index order), then (rest_lo, rest_hi)."""
+        if self._buckets is None:
+            flat = self.flat
+            flows = self.model.layer_Dict["Decoder"].layer_Dict["Flows"]
+            starts = [flat.offset_of(next(iter(blk.parameters()))) for blk in flows]
+            dec_lo = starts[0]
+            last = list(flows[-1].parameters())[-1]
+            dec_hi = flat.offset_of(last) + (last.numel() + 3) // 4 * 4
+            assert all(a < b for a, b in zip(starts, starts[1:])) and dec_hi <= flat.total
+            blocks = [(lo, hi) for lo, hi in zip(starts, starts[1:] + [dec_hi])]
+            rest = [(0, dec_lo)] + ([(dec_hi, flat.total)] if dec_hi < flat.total else [])
+            self._buckets = (blocks, [r for r in rest if r[1] > r[0]])
+        return self._buckets
+
+    def _allreduce_overlapped(self, g):
+        """Called right after loss.backward() has been issued: per-block all-reduces behind the per-block events."""
+        dev = self.device
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(dev)
+        comm, cur = self._comm, torch.cuda.current_stream(dev)
+        blocks, rest = self._grad_buckets()
+        L = _lib.lib()
+        comm.wait_stream(cur)                                  # zero_grad and everything before the backward
+        with torch.cuda.device(dev):
+            for k in reversed(range(len(blocks))):
+                _lib.check(L.glow_flow_wait_block_grads(ctypes.c_void_p(comm.cuda_stream), k), "glow_flow_wait_block_grads")
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(g[blocks[k][0]:blocks[k][1]])
+        _rows.join(dev)                                        # encoder weight gradients (side-stream lanes)
+        _flow.join(dev)
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            for lo, hi in rest:
+                dist.all_reduce(g[lo:hi])
+        cur.wait_stream(comm)
 
     def to_device(self, batch_host):
         """H2D of one collated batch (pinned -> device, async).  Lengths stay on the host too."""
@@ -203,8 +247,11 @@ class TrainStep:
         # encoder weight gradients accumulate straight into the flat gradient buffer on the library's side stream
         # for the duration of THIS step only (joined below, before anything reads the gradients)
         prev_acc, prev_defer = _rows.ACCUMULATE, model.layer_Dict["Decoder"].defer_param_grads
+        prev_fused = _flow.FUSED_PARAM_GRADS
         _rows.ACCUMULATE = True
         model.layer_Dict["Decoder"].defer_param_grads = True
+        if self.overlap_allreduce:
+            _flow.FUSED_PARAM_GRADS = True               # every block's parameter gradients right behind its weight gradients
         try:
             c = 0.5 * math.log(2 * math.pi)
             if geometry is not None:
@@ -235,15 +282,22 @@ class TrainStep:
                     loss = (mle - c) * w_mle + c + mse * w_mse
                 else:
                     loss = mle + mse
+            dec = model.layer_Dict["Decoder"]
+            fused_before = getattr(dec, "fused_backward_calls", 0)
             loss.backward()
-            _rows.join(self.device)                      # encoder weight gradients forked to the side stream
-            _flow.join(self.device)                      # decoder parameter gradients (weight_norm backward)
+            g = self.flat.grad
+            # the per-block events only exist if the decoder's backward really took the per-block path
+            if self.overlap_allreduce and getattr(dec, "fused_backward_calls", 0) == fused_before + 1:
+                self._allreduce_overlapped(g)
+            else:
+                _rows.join(self.device)                  # encoder weight gradients forked to the side stream
+                _flow.join(self.device)                  # decoder parameter gradients (weight_norm backward)
+                if self.world > 1:
+                    dist.all_reduce(g)                   # one collective over the whole flat buffer
         finally:
             _rows.ACCUMULATE = prev_acc
             model.layer_Dict["Decoder"].defer_param_grads = prev_defer
-        g = self.flat.grad
-        if self.world > 1:
-            dist.all_reduce(g)                       # the step's single collective
+            _flow.FUSED_PARAM_GRADS = prev_fused
         if device_schedule:
             self.opt.launch(None)
         else:

@@ -38,6 +38,9 @@ typedef void *glow_stream_t;        /* cudaStream_t */
 #define GLOW_I32   1
 #define GLOW_BF16  2
 #define GLOW_BF16_SIMT 3   /* flow precision only: bf16 storage on the CUDA-core GEMM (device cross-check of GLOW_BF16) */
+#define GLOW_F32_TC 4      /* fp32 storage, tensor-core math at fp32-class accuracy: every operand is split into
+                              bf16 hi + lo parts and each product is three tcgen05 MMAs (hi*hi + lo*hi + hi*lo) with fp32
+                              accumulation in TMEM; exact tanhf / expf epilogues.  The 1e-3 parity mode on tensor cores. */
 
 int         glow_abi_version(void);
 const char *glow_last_error(void);
@@ -211,7 +214,8 @@ typedef struct {
 
 typedef struct {
     glow_flow_config cfg;
-    int       precision;     /* GLOW_F32: fp32 storage + CUDA-core fp32 math (parity mode)
+    int       precision;     /* GLOW_F32_TC: fp32 storage, tcgen05 with the hi/lo operand split (1e-3 parity on tensor cores)
+                                GLOW_F32: fp32 storage + CUDA-core fp32 math (parity mode)
                                 GLOW_BF16: bf16 activations/weights, tcgen05, fp32 accumulate
                                 GLOW_BF16_SIMT: same storage, CUDA-core GEMM (cross-check) */
     int       batch, t_max;  /* mel tensors are [batch, 80, t_max] */
@@ -233,6 +237,9 @@ typedef struct {
 int    glow_flow_param_slots(const glow_flow_config *cfg);
 size_t glow_flow_wpack_floats(const glow_flow_config *cfg);
 size_t glow_flow_wpack_tc_elems(const glow_flow_config *cfg);
+/* bf16 elements of wpack_tc for a precision: 0 for GLOW_F32, the slab images for the bf16 modes, three times that for
+ * GLOW_F32_TC (W_hi, W_hi, W_lo per logical A panel). */
+size_t glow_flow_wpack_tc_elems_for(const glow_flow_config *cfg, int precision);
 /* out[0..3] = elements of ws_f32 (f32), ws_act, bw_f32 (f32), bw_act; the *_act
  * buffers hold f32 (GLOW_F32) or bf16 (GLOW_BF16) elements. */
 int    glow_flow_workspace_elems(const glow_flow_config *cfg, int rows_pad, int batch,
@@ -260,6 +267,13 @@ int    glow_flow_backward(const glow_flow_call *call, const float *dz, const flo
 int    glow_flow_backward_params(const glow_flow_call *call, const float *dz, const float *dlogdet,
                                  float *dwpack, float *dmel, float *dspk,
                                  const float *params, const int64_t *offsets_host, float *grads);
+/*
+ * Data-parallel overlap: after glow_flow_backward_params has been ISSUED, make `stream` wait until block `block`'s
+ * parameter gradients are final in `grads` (blocks finish in the order blocks-1 .. 0).  A communication stream that
+ * waits block by block can all-reduce block k's slice of the flat gradient buffer while blocks k-1 .. 0 are still in
+ * their backward (train.TrainStep; the reference has no data parallelism: SURVEY 8e).  Capturable.
+ */
+int    glow_flow_wait_block_grads(glow_stream_t stream, int block);
 /* dwpack -> gradients of the reference parameters (through weight_norm, exp, logdet), += into grads. */
 int    glow_flow_param_grads(const glow_flow_config *cfg, const float *params,
                              const int64_t *offsets_host, const float *wpack,
@@ -283,6 +297,21 @@ int    glow_flow_pack_rows(const glow_flow_call *call, const float *mel, float *
 int    glow_actnorm_stats(const float *x_rows, const int32_t *row_utt, int rows_pad, int channels,
                           float *out, glow_stream_t stream);
 int    glow_flow_block_forward(const glow_flow_call *call, int block, const float *x_rows, float *z_rows);
+
+/*
+ * Weight gradient of a packed-rows conv on the tensor cores (csrc/wgrad_tc.cuh; autograd's conv backward w.r.t. the
+ * weight for Modules.py:818-852 and :461-573, driven from Train.py:218-231):
+ *     dw[tap][ci][co] (row pitch ldc, tap pitch tap_stride) (+)= sum_r x[r + tap - (taps-1)/2][ci] * g[r][co]
+ * x [rows_pad, ldx] conv input, g [rows_pad, ldg] gradient of the conv output, packed rows (zero guard rows), both
+ * GLOW_BF16, both GLOW_F32 (fp32 operands are rounded to bf16 while they are staged) or both GLOW_F32_TC (fp32
+ * operands split into bf16 hi + lo parts, three MMAs per product); rows with row_utt < 0 are read as zeros when
+ * row_utt is given (fp32 operands).  fp32 accumulation in TMEM over the whole row range.  split: number of row
+ * ranges worked on by different CTAs (<= 0: chosen by the library); accumulate != 0 adds into dw.
+ * Built for (taps, cin) in {(5, k*96), (3, k*96), (1, 80 | 160 | 192)} and cout >= 128, cout % 8 == 0.
+ */
+int    glow_conv_wgrad(const void *x, int x_dtype, int ldx, int cin, const void *g, int ldg, int cout,
+                       const int32_t *row_utt, int rows_pad, int taps, float *dw, int ldc, long long tap_stride,
+                       int accumulate, int split, glow_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * Relative-position multi-head self-attention core

@@ -12,9 +12,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-@pytest.fixture(scope="module", params=list(CASES))
+# fp32: CUDA-core GEMMs.  fp32-tc: the same fp32 storage on tcgen05 with the bf16 hi/lo operand split (three MMAs per
+# product, fp32 accumulate) -- the tensor-core mode that has to meet the same 1e-3.
+@pytest.fixture(scope="module", params=[(n, p) for n in CASES for p in ("fp32", "fp32-tc")], ids=lambda v: "%s-%s" % v)
 def case(request):
-    return load_case(request.param, "fp32")
+    return load_case(request.param[0], request.param[1])
 
 
 def _spk(model, mode, spk):
@@ -175,3 +177,18 @@ def test_training_dropout_masks_agree_between_forward_and_backward():
         lm = float(loss().double())
     fd = (lp - lm) / (2 * eps)
     assert abs(fd - dot) <= 2e-2 * abs(dot), (fd, dot)
+
+
+@pytest.mark.parametrize("mode,tls,mls", [("Vanilla", [23, 17, 9], [140, 96, 50]),
+                                          ("SE", [40, 31, 25, 12, 50], [612, 400, 258, 64, 1000])])
+def test_split_tensor_core_path_matches_cuda_core_fp32(mode, tls, mls):
+    """GLOW_F32_TC (tcgen05, bf16 hi/lo split, own weight-gradient kernel) vs GLOW_F32 (CUDA-core GEMMs, library weight
+    gradients): two independent fp32-class evaluations of the same arithmetic at a second geometry (one that crosses
+    several 128-row tiles); forward / logdet to 1e-4, every parameter gradient to 2e-3, the reverse pass to 1e-3."""
+    z1, ld1, g1, back1 = _fwd_bwd("fp32-tc", mode, 77, tls, mls, 8)
+    z2, ld2, g2, back2 = _fwd_bwd("fp32", mode, 77, tls, mls, 8)
+    assert rel_err(z1, z2) < 1e-4, rel_err(z1, z2)
+    assert rel_err(ld1, ld2) < 1e-4, rel_err(ld1, ld2)
+    assert rel_err(back1, back2) < 1e-3, rel_err(back1, back2)
+    worst = max((rel_err(g1[k], g2[k]), k) for k in g1 if float(g2[k].abs().max()) > 0)
+    assert worst[0] < 2e-3, worst

@@ -369,45 +369,93 @@ colsum_multi_kernel(const __grid_constant__ ColsumJobs<T> jobs, int rows)
     }
 }
 
-// Per-utterance column sums: out[b][n] = sum_{rows of b} D[row, n]  (speaker-bias gradient).
-// grid = (ceil(N/128), B), 128 threads.
+// Per-utterance column sums of the four layers of a block in ONE launch (speaker-bias gradient, Modules.py:863-864):
+//   out[layer][b][n] += sum_{rows of utterance b} D_layer[row, n]
+// grid = (rows_pad / 64, layers), 192 threads, each owning two adjacent columns of a 64-row chunk (a row is read as one
+// contiguous run); rows are sorted by utterance, so a chunk flushes its running sums with one atomicAdd per
+// (utterance it touches, column).  `out` zeroed by the caller.
+constexpr int kSegRows = 64;
 template <typename T>
-static __global__ void __launch_bounds__(128)
-seg_colsum_kernel(const T *__restrict__ D, int ld, int N, const int32_t *__restrict__ utt_off,
-                  const int32_t *__restrict__ utt_len, float *__restrict__ out)
+struct SegColsumJobs {
+    const T *src[kLayers];
+    float *out[kLayers];
+};
+template <typename T>
+static __global__ void __launch_bounds__(192)
+seg_colsum_multi_kernel(const __grid_constant__ SegColsumJobs<T> jobs, const int32_t *__restrict__ row_utt, int rows)
 {
-    const int n = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
-    if (n >= N) return;
-    const int off = utt_off[b], len = utt_len[b];
-    float acc = 0.f;
-    for (int r = 0; r < len; ++r) acc += ldf(D + (size_t)(off + r) * ld + n);
-    out[(size_t)b * N + n] = acc;
+    const T *src = jobs.src[blockIdx.y];
+    float *out = jobs.out[blockIdx.y];
+    const int c2 = threadIdx.x;
+    const int r0 = blockIdx.x * kSegRows, r1 = min(rows, r0 + kSegRows);
+    float a0 = 0.f, a1 = 0.f;
+    int cur = -1;
+    for (int r = r0; r < r1; ++r) {
+        const int u = row_utt[r];
+        if (u != cur) {
+            if (cur >= 0) { atomicAdd(out + (size_t)cur * kG + 2 * c2, a0); atomicAdd(out + (size_t)cur * kG + 2 * c2 + 1, a1); }
+            a0 = a1 = 0.f;
+            cur = u;
+        }
+        if (u < 0) continue;
+        if constexpr (sizeof(T) == 2) {
+            float x, y;
+            unpack_bf16x2(reinterpret_cast<const uint32_t *>(src + (size_t)r * kG)[c2], x, y);
+            a0 += x; a1 += y;
+        } else {
+            const float2 v = reinterpret_cast<const float2 *>(src + (size_t)r * kG)[c2];
+            a0 += v.x; a1 += v.y;
+        }
+    }
+    if (cur >= 0) { atomicAdd(out + (size_t)cur * kG + 2 * c2, a0); atomicAdd(out + (size_t)cur * kG + 2 * c2 + 1, a1); }
 }
 
-// Speaker conditioning backward for one (block, layer):
-//   dW_spk[d][n'] (+)= sum_b emb[b][d] * dspkb[b][n'] ; db_spk[n'] = sum_b dspkb[b][n'] ;
+// Speaker conditioning backward for the four layers of one block (grid = (spk_dim, layers), 128 threads):
+//   dW_spk[d][n'] = sum_b emb[b][d] * dspkb[b][n'] ; db_spk[n'] = sum_b dspkb[b][n'] ;
 //   demb[b][d] += sum_n' dspkb[b][n'] * W_spk[d][n']
-static __global__ void spk_bwd_kernel(const float *__restrict__ emb, int spk_dim, int batch,
-                               const float *__restrict__ dspkb, const float *__restrict__ Wspk,
-                               float *__restrict__ dWspk, float *__restrict__ dbspk, float *__restrict__ demb)
+struct SpkBwdJobs {
+    const float *dspkb[kLayers];     // [B][384]
+    const float *Wspk[kLayers];      // [spk_dim][384]
+    float *dWspk[kLayers], *dbspk[kLayers];
+};
+static __global__ void __launch_bounds__(128)
+spk_bwd_kernel(const float *__restrict__ emb, int spk_dim, int batch, const __grid_constant__ SpkBwdJobs jobs,
+               float *__restrict__ demb)
 {
-    const int d = blockIdx.x, tid = threadIdx.x;     // grid = spk_dim, 384 threads
-    for (int n = tid; n < kG; n += blockDim.x) {
-        float acc = 0.f, accb = 0.f;
-        for (int b = 0; b < batch; ++b) {
-            const float g = dspkb[(size_t)b * kG + n];
-            acc += emb[(size_t)b * spk_dim + d] * g;
-            accb += g;
+    const int d = blockIdx.x, layer = blockIdx.y, tid = threadIdx.x;
+    const float *__restrict__ dspkb = jobs.dspkb[layer];
+    const float *__restrict__ Wspk = jobs.Wspk[layer];
+    float *__restrict__ dWspk = jobs.dWspk[layer], *__restrict__ dbspk = jobs.dbspk[layer];
+    // n = tid, tid + 128, tid + 256: three columns per thread, the batch loop reads coalesced rows of dspkb
+    float acc[3] = {0.f, 0.f, 0.f}, accb[3] = {0.f, 0.f, 0.f};
+    for (int b = 0; b < batch; ++b) {
+        const float e = emb[(size_t)b * spk_dim + d];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float g = dspkb[(size_t)b * kG + tid + 128 * q];
+            acc[q] += e * g;
+            accb[q] += g;
         }
-        dWspk[(size_t)d * kG + n] = acc;
-        if (d == 0) dbspk[n] = accb;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        dWspk[(size_t)d * kG + tid + 128 * q] = acc[q];
+        if (d == 0) dbspk[tid + 128 * q] = accb[q];
     }
     if (demb != nullptr) {
+        __shared__ float part[4];
+        float w[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) w[q] = Wspk[(size_t)d * kG + tid + 128 * q];
         for (int b = 0; b < batch; ++b) {
-            float acc = 0.f;
-            for (int n = tid; n < kG; n += blockDim.x) acc += dspkb[(size_t)b * kG + n] * Wspk[(size_t)d * kG + n];
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if ((tid & 31) == 0) atomicAdd(demb + (size_t)b * spk_dim + d, acc);
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) a += dspkb[(size_t)b * kG + tid + 128 * q] * w[q];
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if ((tid & 31) == 0) part[tid >> 5] = a;
+            __syncthreads();
+            if (tid == 0) atomicAdd(demb + (size_t)b * spk_dim + d, part[0] + part[1] + part[2] + part[3]);
+            __syncthreads();
         }
     }
 }

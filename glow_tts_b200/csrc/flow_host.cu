@@ -60,7 +60,7 @@ static FlowCtx<ActT> make_ctx(const glow_flow_call *call)
     c.wpack_tc = (const __nv_bfloat16 *)call->wpack_tc;
     c.bp = make_block_pack(call->cfg.spk_dim);
     c.bt = make_block_pack_tc(call->precision == GLOW_F32_TC ? 3 : 1);
-    c.wl = make_work_layout(call->cfg.blocks, (size_t)call->rows_pad, call->batch, call->training != 0);
+    c.wl = make_work_layout(call->cfg.blocks, (size_t)call->rows_pad, call->batch, call->training != 0, call->cfg.spk_dim > 0);
     c.ws_f32 = call->ws_f32;
     c.ws_act = (ActT *)call->ws_act;
     c.bw_f32 = call->bw_f32;
@@ -200,7 +200,7 @@ int glow_flow_workspace_elems(const glow_flow_config *cfg, int rows_pad, int bat
     if (rc) return rc;
     GLOW_REQUIRE(out && rows_pad > 0 && rows_pad % kRowTile == 0 && batch >= 1, GLOW_ERR_INVALID,
                  "flow_workspace_elems: bad arguments");
-    const WorkLayout w = make_work_layout(cfg->blocks, (size_t)rows_pad, batch, training != 0);
+    const WorkLayout w = make_work_layout(cfg->blocks, (size_t)rows_pad, batch, training != 0, cfg->spk_dim > 0);
     out[0] = w.f32_total; out[1] = w.act_total; out[2] = w.bwd_f32_total; out[3] = w.bwd_act_total;
     return GLOW_OK;
 }

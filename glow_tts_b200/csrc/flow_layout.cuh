@@ -145,17 +145,19 @@ struct WorkLayout {
     size_t act_total;
     // backward scratch (fp32 then ActT)
     size_t dz, dy;                  // fp32 [rows][160] x2
-    size_t dspkb;                   // fp32 [layers][B][384]
+    size_t dspkb;                   // fp32 [2 sets][layers][B][384]
     size_t bwd_f32_total;
     // ActT, two SETS (block parity): a block's weight-gradient GEMMs run on a side stream while the
     // main stream already computes the next block's data gradients, so the gradients they read must
     // outlive the block: douts [rows][160], dout [rows][192], dh[layer] [rows][192] (d h_i),
-    // dpre[layer] [rows][384] (d gate pre-activation before dropout); dins [rows][384] is main-stream only.
-    size_t douts[2], dout[2], dh[2][kLayers], dpre[2][kLayers], dins;
+    // dpre[layer] [rows][384] (d gate pre-activation before dropout); dins[layer] [rows][384] (the same gradient AFTER
+    // dropout: what the speaker bias sees, Modules.py:862-864; SE mode only) -- read at the end of the block by the
+    // speaker-gradient kernels on the bias-sum stream.
+    size_t douts[2], dout[2], dh[2][kLayers], dpre[2][kLayers], dins[2][kLayers];
     size_t bwd_act_total;
 };
 
-inline WorkLayout make_work_layout(int blocks, size_t rows, int batch, bool training)
+inline WorkLayout make_work_layout(int blocks, size_t rows, int batch, bool training, bool se = true)
 {
     WorkLayout w{};
     const size_t nb = training ? (size_t)blocks : 1;     // inference keeps one block's worth
@@ -177,14 +179,15 @@ inline WorkLayout make_work_layout(int blocks, size_t rows, int batch, bool trai
     w.act_total = o;
     o = 0;
     w.dz = take(rows * kC); w.dy = take(rows * kC);
-    w.dspkb = take((size_t)kLayers * batch * kG);
+    w.dspkb = take((size_t)2 * kLayers * batch * kG);
     w.bwd_f32_total = training ? o : 0;
     o = 0;
     for (int s = 0; s < 2; ++s) {
         w.douts[s] = take(rows * kC); w.dout[s] = take(rows * kH);
         for (int i = 0; i < kLayers; ++i) { w.dh[s][i] = take(rows * kH); w.dpre[s][i] = take(rows * kG); }
     }
-    w.dins = take(rows * kG);
+    for (int s = 0; s < 2; ++s)
+        for (int i = 0; i < kLayers; ++i) w.dins[s][i] = se ? take(rows * kG) : 0;
     w.bwd_act_total = training ? o : 0;
     return w;
 }

@@ -256,7 +256,6 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
     const int R = c.rows.rows_pad, B = c.rows.batch;
     constexpr bool kBf16 = sizeof(ActT) == 2;
     float *DZ = c.bw_f32 + c.wl.dz, *DY = c.bw_f32 + c.wl.dy;
-    ActT *DINS = c.bw_act + c.wl.dins;
     SideStream *ss = nullptr;
     GLOW_TRY(side_stream(&ss));
     cudaStream_t side = ss->stream;
@@ -337,17 +336,9 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
         for (int i = kLayers - 1; i >= 0; --i) {
             const bool last = i == kLayers - 1;
             const ActT *DHnext = last ? nullptr : DH[i + 1];
-            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, c.spk != nullptr ? DINS : nullptr, DPRE[i]));
-            if (c.spk != nullptr) {
-                float *dspkb = c.bw_f32 + c.wl.dspkb;
-                seg_colsum_kernel<ActT><<<dim3(kG / 128, B), 128, 0, c.st>>>(DINS, kG, kG, c.rows.utt_off,
-                                                                            c.rows.utt_len, dspkb);
-                GLOW_CHECK_LAUNCH("seg_colsum_kernel");
-                spk_bwd_kernel<<<c.cfg.spk_dim, 128, 0, c.st>>>(c.spk, c.cfg.spk_dim, B, dspkb,
-                                                               c.wpack + (size_t)k * c.bp.total + c.bp.spk_w[i],
-                                                               dwp + c.bp.spk_w[i], dwp + c.bp.spk_b[i], dspk);
-                GLOW_CHECK_LAUNCH("spk_bwd_kernel");
-            }
+            // SE: d(gate pre-activation AFTER dropout) is what the speaker bias sees (Modules.py:862-864); it is kept per
+            // layer and reduced at the end of the block, off the data-gradient chain (below, bias-sum stream)
+            GLOW_TRY(Ops::b_rs(c, k, i, b, DHnext, DOUT, c.spk != nullptr ? c.bw_act + c.wl.dins[set][i] : nullptr, DPRE[i]));
             GLOW_TRY(Ops::b_in(c, k, i, DPRE[i], DHnext, DH[i]));
             if (!own || i == 0) GLOW_TRY(fork());          // DPRE[i], DH[i] are final
             // dW_in[tap][192][384] = H_i[row + tap - 2]^T DPRE[row]
@@ -384,6 +375,25 @@ int flow_backward_impl(const FlowCtx<ActT> &c, const float *dz, int T, const flo
             GLOW_CHECK_CUDA(cudaStreamWaitEvent(ss->aux, ss->aux_fork, 0));
             colsum_multi_kernel<ActT><<<dim3(R / 128, cj.count), 192, 0, ss->aux>>>(cj, R);
             GLOW_CHECK_LAUNCH("colsum_multi_kernel");
+            if (c.spk != nullptr) {
+                // speaker conditioning of the block's four layers: per-utterance sums of d(ins) -> dW_spk, db_spk, d(emb)
+                float *dspkb = c.bw_f32 + c.wl.dspkb + (size_t)set * kLayers * B * kG;
+                GLOW_CHECK_CUDA(cudaMemsetAsync(dspkb, 0, sizeof(float) * kLayers * B * kG, ss->aux));
+                SegColsumJobs<ActT> sj{};
+                SpkBwdJobs pj{};
+                for (int i = 0; i < kLayers; ++i) {
+                    sj.src[i] = c.bw_act + c.wl.dins[set][i];
+                    sj.out[i] = dspkb + (size_t)i * B * kG;
+                    pj.dspkb[i] = sj.out[i];
+                    pj.Wspk[i] = c.wpack + (size_t)k * c.bp.total + c.bp.spk_w[i];
+                    pj.dWspk[i] = dwp + c.bp.spk_w[i];
+                    pj.dbspk[i] = dwp + c.bp.spk_b[i];
+                }
+                seg_colsum_multi_kernel<ActT><<<dim3(R / kSegRows, kLayers), 192, 0, ss->aux>>>(sj, c.rows.row_utt, R);
+                GLOW_CHECK_LAUNCH("seg_colsum_multi_kernel");
+                spk_bwd_kernel<<<dim3(c.cfg.spk_dim, kLayers), 128, 0, ss->aux>>>(c.spk, c.cfg.spk_dim, B, pj, dspk);
+                GLOW_CHECK_LAUNCH("spk_bwd_kernel");
+            }
             GLOW_CHECK_CUDA(cudaEventRecord(ss->aux_done[set], ss->aux));
         }
         for (int l = 1; l < kWgLanes; ++l) {               // lanes join lane 0 (== side)

@@ -2,7 +2,7 @@
 //
 // Replaces the per-parameter Python loop of Radam.py:25-90 (fp32 temp copies, ~10 tiny
 // kernels per tensor x 515 tensors) and torch.nn.utils.clip_grad_norm_ (Train.py:227-231):
-//   glow_sqnorm      : sum g^2 over the flat gradient buffer (one float, atomics)
+//   glow_sqnorm      : sum g^2 over the flat gradient buffer (one float, fixed summation order)
 //   glow_radam_step  : clip (coef = min(1, max_norm / (||g|| + 1e-6))) + RAdam update
 // The rectification scalars (N_sma, step_size) and the Noam learning rate are host
 // scalars, exactly as Radam.py:57-76 / Noam_Scheduler.py:17-29 compute them.
@@ -10,10 +10,16 @@
 
 namespace glow {
 
+// Deterministic: every CTA leaves its partial sum in partial[blockIdx.x]; the last CTA to finish adds the partials in
+// a fixed order.  The grid only depends on n, so two runs -- or two data-parallel ranks holding the same all-reduced
+// gradient -- get the SAME bits, hence the same clip coefficient and the same update (an atomicAdd of the partials
+// made the coefficient differ in the last bits from rank to rank: replicas would drift apart).
 __global__ void __launch_bounds__(256)
-sqnorm_kernel(const float *__restrict__ g, size_t n, float *__restrict__ out)
+sqnorm_kernel(const float *__restrict__ g, size_t n, float *__restrict__ partial, unsigned int *__restrict__ counter,
+              float *__restrict__ out)
 {
     __shared__ float s[8];
+    __shared__ bool s_last;
     float acc = 0.f;
     const size_t n4 = n >> 2;
     const float4 *g4 = reinterpret_cast<const float4 *>(g);
@@ -30,7 +36,24 @@ sqnorm_kernel(const float *__restrict__ g, size_t n, float *__restrict__ out)
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s[i];
-        atomicAdd(out, t);
+        partial[blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float t = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += reinterpret_cast<volatile float *>(partial)[i];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) total += s[i];
+        *out = total;
+        *counter = 0u;                   // ready for the next launch (stream-ordered)
     }
 }
 
@@ -104,10 +127,22 @@ int glow_sqnorm(const float *g, size_t n, float *out, glow_stream_t stream)
     GLOW_REQUIRE(g && out, GLOW_ERR_INVALID, "sqnorm: null pointer");
     GLOW_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, GLOW_ERR_INVALID, "sqnorm: g must be 16 B aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    GLOW_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-    if (n == 0) return GLOW_OK;
+    if (n == 0) {
+        GLOW_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+        return GLOW_OK;
+    }
+    // per-device scratch for the partial sums + the arrival counter (allocated on first use: an eager warm-up call,
+    // never under stream capture); launches on one device are stream-ordered by the caller
+    static float *scratch[kMaxDevices] = {};
+    int dev = 0;
+    GLOW_CHECK_CUDA(cudaGetDevice(&dev));
+    GLOW_REQUIRE(dev >= 0 && dev < kMaxDevices, GLOW_ERR_UNSUPPORTED, "sqnorm: device index %d", dev);
+    if (scratch[dev] == nullptr) {
+        GLOW_CHECK_CUDA(cudaMalloc(&scratch[dev], sizeof(float) * (kNumSMs * 8 + 4)));
+        GLOW_CHECK_CUDA(cudaMemset(scratch[dev], 0, sizeof(float) * (kNumSMs * 8 + 4)));
+    }
     const int grid = (int)((n / 4 + 255) / 256 < (size_t)(kNumSMs * 8) ? (n / 4 + 255) / 256 + 1 : kNumSMs * 8);
-    sqnorm_kernel<<<grid, 256, 0, st>>>(g, n, out);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(g, n, scratch[dev] + 4, reinterpret_cast<unsigned int *>(scratch[dev]), out);
     GLOW_CHECK_LAUNCH("sqnorm_kernel");
     return GLOW_OK;
 }

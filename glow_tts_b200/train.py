@@ -212,7 +212,9 @@ class TrainStep:
         comm, cur = self._comm, torch.cuda.current_stream(dev)
         blocks, rest = self._grad_buckets()
         L = _lib.lib()
-        comm.wait_stream(cur)                                  # zero_grad and everything before the backward
+        # no comm.wait_stream(cur) here: the whole backward is already queued on `cur`, waiting for its tail would
+        # serialise the buckets behind it.  Each bucket waits for its own block's event instead, which is ordered
+        # after this step's zero_grad through the backward itself.
         with torch.cuda.device(dev):
             for k in reversed(range(len(blocks))):
                 _lib.check(L.glow_flow_wait_block_grads(ctypes.c_void_p(comm.cuda_stream), k), "glow_flow_wait_block_grads")
@@ -347,9 +349,15 @@ class GraphedTrainStep:
                  t_text_pad=None, t_mel_pad=None):
         self.step, self.device = step, step.device
         pat = getattr(step.hp.Train, "Train_Pattern", None)
-        self.t_text = int(t_text_pad) if t_text_pad else (int(pat.Text_Length.Max) + 2 if pat else 202)
-        self.t_mel = int(t_mel_pad) if t_mel_pad else (int(pat.Mel_Length.Max) if pat else 1000)
-        self.t_mel += self.t_mel % 2
+        t_text = int(t_text_pad) if t_text_pad else (int(pat.Text_Length.Max) + 2 if pat else 202)
+        t_mel = int(t_mel_pad) if t_mel_pad else (int(pat.Mel_Length.Max) if pat else 1000)
+        t_mel += t_mel % 2
+        # padded sizes a batch may be given: the smallest menu entry that holds its longest item.  Padding is cheap for
+        # the packed-row kernels (they never touch it) but not for what runs on [B, C, T] tensors (alignment search,
+        # path expansion, losses, the torch-side glue), so short-utterance batches (VCTK-shaped) get smaller shapes.
+        self.text_menu = [t_text] if t_text_pad else sorted({max(8, (t_text * q // 4 + 7) // 8 * 8) for q in (1, 2, 3)} | {t_text})
+        self.mel_menu = [t_mel] if t_mel_pad else sorted({max(64, (t_mel * q // 4 + 63) // 64 * 64) for q in (1, 2, 3)} | {t_mel})
+        self.t_text, self.t_mel = t_text, t_mel
         self.gf, self.gp = global_frames, global_positions
         self.buckets = {}
         self._inputs = {}                      # batch size -> static (tokens, mels, spk)
@@ -370,8 +378,12 @@ class GraphedTrainStep:
 
     # ------------------------------------------------------------------ buckets
     def bucket_key(self, tl, ml):
-        return _geo.StepGeometry.bucket_of([int(v) for v in tl.tolist()], [int(v) for v in ml.tolist()],
-                                           self.t_text, self.t_mel)
+        tl, ml = [int(v) for v in tl.tolist()], [int(v) for v in ml.tolist()]
+        tt = next((t for t in self.text_menu if t >= max(tl)), None)
+        tm = next((t for t in self.mel_menu if t >= max(ml)), None)
+        if tt is None or tm is None:
+            raise ValueError("batch exceeds the padded sizes (%d tokens, %d mel frames)" % (self.t_text, self.t_mel))
+        return _geo.StepGeometry.bucket_of(tl, ml, tt, tm)
 
     @property
     def key(self):
@@ -400,15 +412,20 @@ class GraphedTrainStep:
             bk = self.buckets[key] = _Bucket(_geo.StepGeometry(b, tt, tm, rd, re, self.device))
         return bk
 
+    def _shape_key(self, batch_host):
+        key = self.bucket_key(batch_host[1], batch_host[3])
+        return (key[0], key[3], key[4])                          # (batch, T_text_pad, T_mel_pad)
+
     def _static_inputs(self, batch_host):
         tokens, _, mels, _, spk = batch_host
-        b = tokens.shape[0]
-        if b not in self._inputs:
+        k = self._shape_key(batch_host)
+        if k not in self._inputs:
             dev = self.device
-            self._inputs[b] = (torch.ones((b, self.t_text), dtype=tokens.dtype, device=dev),
-                               torch.full((b, mels.shape[1], self.t_mel), -4.0, dtype=mels.dtype, device=dev),
+            b, tt, tm = k
+            self._inputs[k] = (torch.ones((b, tt), dtype=tokens.dtype, device=dev),
+                               torch.full((b, mels.shape[1], tm), -4.0, dtype=mels.dtype, device=dev),
                                torch.zeros((b,), dtype=spk.dtype, device=dev))
-        return self._inputs[b]
+        return self._inputs[k]
 
     def load(self, batch_host):
         """Refresh the static input buffers (async H2D when the host tensors are pinned).  Positions beyond the
@@ -425,7 +442,7 @@ class GraphedTrainStep:
         step in flight (what a data loader's pinned, non_blocking prefetch does).  `run(batch_host)` with the same
         object then only moves staging -> static buffers on the device."""
         tokens, _, mels, _, spk = batch_host
-        b = tokens.shape[0]
+        b = self._shape_key(batch_host)
         self._static_inputs(batch_host)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -449,7 +466,7 @@ class GraphedTrainStep:
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(self._staged_ready)
             st, sm, ss = self._static_inputs(batch_host)
-            gt, gm, gs = self._staging[tokens.shape[0]]
+            gt, gm, gs = self._staging[self._shape_key(batch_host)]
             st[:, :tokens.shape[1]].copy_(gt[:, :tokens.shape[1]], non_blocking=True)
             sm[:, :, :mels.shape[2]].copy_(gm[:, :, :mels.shape[2]], non_blocking=True)
             ss.copy_(gs, non_blocking=True)

@@ -45,11 +45,21 @@ def _worker(rank, world, port, q):
         batch = synth_batch(10 + rank, *geos[rank])
         gf, gp = 140 + 96 + 50 + 180 + 70 + 120, 6 * 30
         grads = {}
+
+        def across_ranks(g):
+            """(number of elements that differ from rank 0's copy, first and last such index)"""
+            peer = g.clone()
+            dist.broadcast(peer, src=0)
+            bad = (peer != g).nonzero().flatten()
+            return (int(bad.numel()), int(bad[0]) if bad.numel() else -1, int(bad[-1]) if bad.numel() else -1)
+
+        diag = {}
         for overlap in (True, False):
             step.overlap_allreduce = overlap
             step.run(step.to_device(batch), global_frames=gf, global_positions=gp)
             torch.cuda.synchronize()
             grads[overlap] = step.flat.grad.detach().clone()
+            diag["eager_overlap" if overlap else "eager_single"] = across_ranks(grads[overlap])
         scale = float(grads[False].abs().max())
         err = float((grads[True] - grads[False]).abs().max()) / scale
         # replayed from a captured graph (the bucketed all-reduces are graph nodes on the communication stream)
@@ -62,9 +72,9 @@ def _worker(rank, world, port, q):
         g_graph = step.flat.grad.detach().clone()
         err_graph = float((g_graph - grads[False]).abs().max()) / scale
         # every rank must hold the same reduced gradient
-        peer = g_graph.clone()
-        dist.broadcast(peer, src=0)
-        same = bool(torch.equal(peer, g_graph))
+        diag["graph_overlap"] = across_ranks(g_graph)
+        diag["buckets"] = step._grad_buckets()
+        same = diag
         graphed.buckets.clear()
         graphed.current = None
         torch.cuda.synchronize()
@@ -90,4 +100,5 @@ def test_bucketed_allreduce_matches_the_single_allreduce():
         assert scale > 0
         assert err < 2e-3, (rank, err)                           # bf16 weight gradients: split order differs slightly
         assert err_graph < 2e-3, (rank, err_graph)
-        assert same, rank
+        for name in ("eager_single", "eager_overlap", "graph_overlap"):
+            assert same[name][0] == 0, (rank, name, same)           # the reduced gradient is identical on every rank

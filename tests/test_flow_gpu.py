@@ -44,8 +44,12 @@ def test_reverse_matches_reference_and_inverts(case):
         zin = torch.from_numpy(g["dec_z"]).cuda()
         back, ld, _ = dec(zin, m, _spk(model, mode, spk), reverse=True)
     assert ld is None
-    assert rel_err(back.cpu(), g["dec_reverse_of_z"]) < 2e-3    # inverse amplifies fp32 rounding (see test_oracle_model)
-    assert rel_err(back.cpu(), (mels * m.cpu())) < 2e-3          # Decoder(reverse) o Decoder == id
+    # The inverse of this synthetic fixture is ill-conditioned: it amplifies any forward-side rounding ~500x (two fp32
+    # evaluations with different op order already differ by 5e-4: tests/test_oracle_model.py).  fp32: 2e-3.  fp32-tc
+    # carries 2^-16 per product (measured forward error 2e-5 -> reverse 1.5e-2): 3e-2.
+    tol = 2e-3 if dec.precision == "fp32" else 3e-2
+    assert rel_err(back.cpu(), g["dec_reverse_of_z"]) < tol
+    assert rel_err(back.cpu(), (mels * m.cpu())) < tol           # Decoder(reverse) o Decoder == id
 
 
 def test_backward_matches_reference(case):
@@ -184,11 +188,11 @@ def test_training_dropout_masks_agree_between_forward_and_backward():
 def test_split_tensor_core_path_matches_cuda_core_fp32(mode, tls, mls):
     """GLOW_F32_TC (tcgen05, bf16 hi/lo split, own weight-gradient kernel) vs GLOW_F32 (CUDA-core GEMMs, library weight
     gradients): two independent fp32-class evaluations of the same arithmetic at a second geometry (one that crosses
-    several 128-row tiles); forward / logdet to 1e-4, every parameter gradient to 2e-3, the reverse pass to 1e-3."""
+    several 128-row tiles); forward / logdet to 1e-4, every parameter gradient to 2e-3, the reverse pass to 3e-2."""
     z1, ld1, g1, back1 = _fwd_bwd("fp32-tc", mode, 77, tls, mls, 8)
     z2, ld2, g2, back2 = _fwd_bwd("fp32", mode, 77, tls, mls, 8)
     assert rel_err(z1, z2) < 1e-4, rel_err(z1, z2)
     assert rel_err(ld1, ld2) < 1e-4, rel_err(ld1, ld2)
-    assert rel_err(back1, back2) < 1e-3, rel_err(back1, back2)
+    assert rel_err(back1, back2) < 3e-2, rel_err(back1, back2)      # ill-conditioned inverse, see above
     worst = max((rel_err(g1[k], g2[k]), k) for k in g1 if float(g2[k].abs().max()) > 0)
     assert worst[0] < 2e-3, worst

@@ -11,11 +11,17 @@ import bench
 from glow_tts_b200.train import TrainStep, GraphedTrainStep
 from torch.profiler import profile, ProfilerActivity
 
-model, hp = bench.build_cpu_model("Vanilla", "bf16")
+def _arg(name, default):
+    return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else default
+
+
+# --mode SE --kind ljvctk --batch 64: BASELINE configs[2] on one GPU
+MODE, KIND, BATCH = _arg("--mode", "Vanilla"), _arg("--kind", "lj"), int(_arg("--batch", "32"))
+model, hp = bench.build_cpu_model(MODE, _arg("--precision", "bf16"))
 dev = torch.device("cuda:0")
 model = model.to(dev).train()
 step = TrainStep(model, hp, dev)
-host = bench.workload_batch("lj", 32, 0)
+host = bench.workload_batch(KIND, BATCH, 0)
 for _ in range(3):
     step.run(step.to_device(host))
 g = GraphedTrainStep(step, host, warmup=1)
@@ -57,7 +63,7 @@ print("\nGPU idle (no kernel on any stream): %.3f ms" % (idle / 1e3))
 fam = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:
     n = e["name"]
-    for key in ("tc_gemm3_kernel", "nvjet", "colsum", "rpr_attn", "elementwise", "cutlass", "layer_norm", "LayerNorm",
+    for key in ("tc_gemm3_kernel", "wgrad_tc_kernel", "nvjet", "colsum", "rpr_attn", "elementwise", "cutlass", "layer_norm", "LayerNorm",
                 "GammaBeta", "index", "gather", "reduce_kernel", "wn_pack", "wn_grad", "rows_pack", "mas_kernel",
                 "radam", "mix_bwd", "dropout", "Memset", "Memcpy"):
         if key in n:

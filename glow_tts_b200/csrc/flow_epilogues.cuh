@@ -243,8 +243,15 @@ struct EpiGate {
     // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
     template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
     {
+        float acts[NV / 2];
+        apply_acts<NV>(row, utt, n0, v, acts);
+    }
+    // the same, handing the NV / 2 gated activations back to the caller as well (flow_tc_layer.cuh keeps them in shared
+    // memory as the A operand of the res/skip GEMM)
+    template <int NV> __device__ __forceinline__ void apply_acts(int row, int utt, int n0, const float *v, float (&acts)[NV / 2]) const
+    {
         const bool m = utt >= 0;
-        float pre[NV], ts[NV], acts[NV / 2];
+        float pre[NV], ts[NV];
         ld_ro<NV>(bias + n0, pre);
 #pragma unroll
         for (int j = 0; j < NV; ++j) pre[j] += v[j];

@@ -467,25 +467,14 @@ struct TcOps {
         return gemm_tc3<kH, kBnH, kCh, 1, kCh, 1, 0, kCh, 0>(one(b.YA), ws(c, k) + c.bt.start_w, c.rows.row_utt,
                                                           c.rows.rows_pad, e, c.st, "start");
     }
-    static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
+    static int layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP);      // below: needs flow_tc_layer.cuh
+    static int layer_two_launches(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
     {
         const bool last = i == kLayers - 1;
         EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt,
                                drop_cfg(c, k, i)};
-        // GLOW_IN_GATE_PANEL=96: two 96-channel A panels and a 5-stage weight ring instead of one 192-channel panel
-        // and 3 stages (the b_in trade).  Opt-in only: one probe at the end of round 1 showed no gain
-        // (step 6.29 vs 6.31 ms, in_gate 1.04 vs 1.01 ms per step in the bench hook) -- unlike b_in, in_gate's MMA loop
-        // is not paced by the ring -- and it has not been through tests/test_flow_gpu.py with the variable set.
-        static const bool split_panels = [] { const char *e = getenv("GLOW_IN_GATE_PANEL"); return e && atoi(e) == 96; }();
-        int rc;
-        if (split_panels) {
-            TcA a2{{b.H[i], b.H[i] + 96, nullptr, nullptr}};
-            rc = gemm_tc3<kG, kBnGate, 96, 2, kH, kTaps, +1, kTcKs, 0>(a2, ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
-                                                                   c.rows.rows_pad, eg, c.st, "in_gate");
-        } else {
-            rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs, 0>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
+        int rc = gemm_tc3<kG, kBnGate, kH, 1, kH, kTaps, +1, kTcKs, 0>(one(b.H[i]), ws(c, k) + c.bt.in_w[i], c.rows.row_utt,
                                                                     c.rows.rows_pad, eg, c.st, "in_gate");
-        }
         if (rc) return rc;
         EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT,
                             c.rows.row_utt, i == 0, last};
@@ -536,6 +525,28 @@ struct TcOps {
                                                               c.rows.rows_pad, e, c.st, "b_start");
     }
 };
+
+}  // namespace glow
+
+#include "flow_tc_layer.cuh"
+
+namespace glow {
+
+// One WaveNet layer = ONE launch (flow_tc_layer.cuh); GLOW_FUSED_LAYER=0 puts the two stand-alone GEMM launches back.
+template <bool FAST>
+int TcOps<FAST>::layer(const Ctx &c, int k, int i, const Bufs<ActT> &b, float *SKIP)
+{
+    const char *env = getenv("GLOW_FUSED_LAYER");          // read per call: tests flip it inside one process
+    if (env != nullptr && atoi(env) == 0) return layer_two_launches(c, k, i, b, SKIP);
+    const bool last = i == kLayers - 1;
+    EpiGate<ActT, FAST> eg{wp(c, k) + c.bp.in_b[i], spkb_ptr(c, k, i), b.TS[i], b.ACTS[i], c.rows.row_utt, drop_cfg(c, k, i)};
+    EpiResSkip<ActT> er{wp(c, k) + c.bp.rs_b[i], b.H[i], last ? nullptr : b.H[i + 1], SKIP, b.OUT, c.rows.row_utt, i == 0, last};
+    if (last)
+        return layer_tc<kH, kBnH, 64, FAST>(b.H[i], ws(c, k) + c.bt.in_w[i], ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+                                            c.rows.rows_pad, eg, er, c.st);
+    return layer_tc<kG, kBnGate, kTcKs, FAST>(b.H[i], ws(c, k) + c.bt.in_w[i], ws(c, k) + c.bt.rs_w[i], c.rows.row_utt,
+                                              c.rows.rows_pad, eg, er, c.st);
+}
 
 // ------------------------------------------------------- tensor-core ops at fp32-class accuracy --
 // GLOW_F32_TC: fp32 activations, every GEMM as three bf16 tcgen05 MMAs per product (AMODE 2 above), exact tanhf /

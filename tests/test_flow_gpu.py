@@ -196,3 +196,22 @@ def test_split_tensor_core_path_matches_cuda_core_fp32(mode, tls, mls):
     assert rel_err(back1, back2) < 3e-2, rel_err(back1, back2)      # ill-conditioned inverse, see above
     worst = max((rel_err(g1[k], g2[k]), k) for k in g1 if float(g2[k].abs().max()) > 0)
     assert worst[0] < 2e-3, worst
+
+
+@pytest.mark.parametrize("mode,tls,mls", [("Vanilla", [23, 17, 9], [140, 96, 50]),
+                                          ("SE", [40, 31, 25, 12, 50], [612, 400, 258, 64, 1000])])
+def test_fused_layer_kernel_equals_the_two_launches(mode, tls, mls, monkeypatch):
+    """flow_tc_layer.cuh (gate GEMM -> tanh * sigmoid kept in shared memory -> res/skip GEMM, one launch per WaveNet
+    layer) against the two stand-alone GEMM launches (GLOW_FUSED_LAYER=0): the same MMAs in the same order on the
+    same bf16 operands, so forward, reverse and every gradient agree to accumulation noise (1e-5 of the largest
+    entry; the saved activations the backward reads are written by the same epilogue functor)."""
+    monkeypatch.setenv("GLOW_FUSED_LAYER", "0")
+    z2, ld2, g2, back2 = _fwd_bwd("bf16", mode, 77, tls, mls, 8)
+    monkeypatch.setenv("GLOW_FUSED_LAYER", "1")
+    z1, ld1, g1, back1 = _fwd_bwd("bf16", mode, 77, tls, mls, 8)
+    assert torch.isfinite(z1).all()
+    assert rel_err(z1, z2) < 1e-5, rel_err(z1, z2)
+    assert rel_err(ld1, ld2) < 1e-5, rel_err(ld1, ld2)
+    assert rel_err(back1, back2) < 1e-5, rel_err(back1, back2)
+    worst = max((rel_err(g1[k], g2[k]), k) for k in g1 if float(g2[k].abs().max()) > 0)
+    assert worst[0] < 1e-4, worst

@@ -400,7 +400,9 @@ def run_own(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that cannot complete must fail in minutes, not after NCCL's 10-minute default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _lib.lib()
 
     tb = TrainBench(args, args.mode, args.kind, args.batch, args.geometries, False, world, rank, dev)

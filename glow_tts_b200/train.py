@@ -184,8 +184,12 @@ class TrainStep:
         # Data parallelism: the flat gradient buffer is all-reduced in BUCKETS -- one per decoder block, issued on a
         # communication stream as soon as that block's parameter gradients are final (glow_flow_wait_block_grads), so
         # block k's reduction runs while blocks k-1 .. 0 are still in their backward; the encoder's slice goes last.
-        # GLOW_ALLREDUCE_OVERLAP=0: one all-reduce of the whole buffer after the backward (round 1; fully exposed).
-        self.overlap_allreduce = self.world > 1 and os.environ.get("GLOW_ALLREDUCE_OVERLAP", "1") != "0"
+        # OPT-IN (GLOW_ALLREDUCE_OVERLAP=1), eager steps only: verified on 2 GPUs (tests/test_ddp_nccl_gpu.py: same
+        # gradients as the single all-reduce, bit-identical across ranks), but the one 8-GPU run this round could afford
+        # deadlocked with the buckets captured inside lazily built per-bucket graphs (ranks capture at different steps;
+        # profiles/README.md), so the default is ONE all-reduce of the whole buffer after the backward, issued eagerly
+        # BETWEEN the two captured halves of the step (GraphedTrainStep) -- no collective lives inside a CUDA graph.
+        self.overlap_allreduce = self.world > 1 and os.environ.get("GLOW_ALLREDUCE_OVERLAP", "0") == "1"
         self._comm = None
         self._buckets = None
 
@@ -235,8 +239,11 @@ class TrainStep:
         return (tokens.to(dev, non_blocking=True), tl, mels.to(dev, non_blocking=True), ml,
                 spk.to(dev, non_blocking=True))
 
-    def run(self, batch, global_frames=None, global_positions=None, device_schedule=False, geometry=None):
-        """batch = (tokens, token_lengths(host), mels, mel_lengths(host), speakers) with tensors on
+    def run(self, batch, global_frames=None, global_positions=None, device_schedule=False, geometry=None, phase="all"):
+        """phase: "all" (default) the whole step; "backward": zero_grad .. backward + joins, NO collective, NO update
+        (GraphedTrainStep under data parallelism captures this half and `update()` separately and issues the
+        all-reduce eagerly between the two replays).
+        batch = (tokens, token_lengths(host), mels, mel_lengths(host), speakers) with tensors on
         the device.  Under data parallelism pass the GLOBAL frame count and B*T_x,max so each
         rank's loss is weighted to reproduce the single-process global-batch loss.
         device_schedule=True leaves the optimizer scalars to `opt.hyper_dev` (GraphedTrainStep).
@@ -252,7 +259,7 @@ class TrainStep:
         prev_fused = _flow.FUSED_PARAM_GRADS
         _rows.ACCUMULATE = True
         model.layer_Dict["Decoder"].defer_param_grads = True
-        if self.overlap_allreduce:
+        if self.overlap_allreduce and phase == "all":
             _flow.FUSED_PARAM_GRADS = True               # every block's parameter gradients right behind its weight gradients
         try:
             c = 0.5 * math.log(2 * math.pi)
@@ -289,24 +296,30 @@ class TrainStep:
             loss.backward()
             g = self.flat.grad
             # the per-block events only exist if the decoder's backward really took the per-block path
-            if self.overlap_allreduce and getattr(dec, "fused_backward_calls", 0) == fused_before + 1:
+            if (phase == "all" and self.overlap_allreduce
+                    and getattr(dec, "fused_backward_calls", 0) == fused_before + 1):
                 self._allreduce_overlapped(g)
             else:
                 _rows.join(self.device)                  # encoder weight gradients forked to the side stream
                 _flow.join(self.device)                  # decoder parameter gradients (weight_norm backward)
-                if self.world > 1:
+                if self.world > 1 and phase == "all":
                     dist.all_reduce(g)                   # one collective over the whole flat buffer
         finally:
             _rows.ACCUMULATE = prev_acc
             model.layer_Dict["Decoder"].defer_param_grads = prev_defer
             _flow.FUSED_PARAM_GRADS = prev_fused
+        self.last = {"loss": loss.detach(), "mle": mle.detach(), "mse": mse.detach(),
+                     "grad_norm": self.opt.grad_norm}
+        if phase == "all":
+            self.update(device_schedule)
+        return self.last["loss"]
+
+    def update(self, device_schedule=False):
+        """clip + RAdam + Noam over the (all-reduced) flat gradient buffer."""
         if device_schedule:
             self.opt.launch(None)
         else:
             self.opt.step(grad_scale=1.0 / self.world)
-        self.last = {"loss": loss.detach(), "mle": mle.detach(), "mse": mse.detach(),
-                     "grad_norm": self.opt.grad_norm}
-        return self.last["loss"]
 
     def loss_scalars(self, tl, ml, global_frames=None, global_positions=None):
         """Host side of the geometry's loss scalars for one batch: [1/(B*T_x,max), w_mle, w_mse]."""
@@ -367,6 +380,13 @@ class GraphedTrainStep:
         self._pool = None
         self.current = None                    # bucket of the most recent step
         self.warmup_last = {}
+        # Data parallelism: NO collective inside a captured graph.  Ranks build their per-bucket graphs at different
+        # steps (their batches differ), and a graph that replays NCCL kernels on one rank while another rank issues
+        # the same collective eagerly (or captures) is exactly the mix NCCL's ordering rules make fragile.  So a
+        # bucket's graph ends before the all-reduce; the all-reduce is issued eagerly; clip + RAdam is a second,
+        # bucket-independent graph.
+        self.split = step.world > 1
+        self._opt_graph = None
         step.opt.use_device_schedule()
         if batch_host is not None:
             # constructor contract of round 1: `warmup` eager steps on the example batch (handles, caches, ActNorm
@@ -491,7 +511,7 @@ class GraphedTrainStep:
         opt = self.step.opt
         opt.upload(opt.advance(1.0 / self.step.world))
         with _lib.capture_keepalive() as keep:
-            loss = self.step.run(dev_batch, device_schedule=True, geometry=bk.geo)
+            loss = self.step.run(dev_batch, global_frames, global_positions, device_schedule=True, geometry=bk.geo)
         bk.keep.extend(keep)
         bk.last = dict(self.step.last)
         bk.loss = loss
@@ -513,7 +533,12 @@ class GraphedTrainStep:
         cap = torch.cuda.Stream(dev, priority=prio) if prio != 0 else torch.cuda.Stream(dev)
         with _lib.capture_keepalive() as keep:
             with torch.cuda.graph(graph, pool=self._pool, stream=cap):
-                loss = self.step.run(bk._dev_batch, device_schedule=True, geometry=bk.geo)
+                loss = self.step.run(bk._dev_batch, device_schedule=True, geometry=bk.geo,
+                                     phase="backward" if self.split else "all")
+            if self.split and self._opt_graph is None:           # clip + RAdam: one graph for every bucket
+                self._opt_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._opt_graph, pool=self._pool, stream=cap):
+                    self.step.update(device_schedule=True)
         bk.keep.extend(keep)
         # the graph's result tensors are placeholders until its first replay: give them the eager step's results
         eager_loss, eager_last = bk.loss, bk.last
@@ -542,5 +567,8 @@ class GraphedTrainStep:
         opt = self.step.opt
         opt.upload(opt.advance(1.0 / self.step.world))
         bk.graph.replay()
+        if self.split:
+            dist.all_reduce(self.step.flat.grad)                 # eager, between the two captured halves
+            self._opt_graph.replay()
         bk.replays += 1
         return bk.loss

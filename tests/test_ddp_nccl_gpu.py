@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
     try:
         from glow_tts_b200 import modules
         from glow_tts_b200.hparams import load_hparams
@@ -40,7 +41,7 @@ def _worker(rank, world, port, q):
         step = TrainStep(model, hp, dev)
         step.opt.lr0 = 0.0
         step.opt.wd = 0.0                                        # parameters stay put: gradients are comparable
-        assert step.overlap_allreduce
+        assert not step.overlap_allreduce                       # opt-in (GLOW_ALLREDUCE_OVERLAP=1)
         geos = [([23, 17, 9], [140, 96, 50]), ([30, 12, 21], [180, 70, 120])]
         batch = synth_batch(10 + rank, *geos[rank])
         gf, gp = 140 + 96 + 50 + 180 + 70 + 120, 6 * 30
@@ -62,9 +63,11 @@ def _worker(rank, world, port, q):
             diag["eager_overlap" if overlap else "eager_single"] = across_ranks(grads[overlap])
         scale = float(grads[False].abs().max())
         err = float((grads[True] - grads[False]).abs().max()) / scale
-        # replayed from a captured graph (the bucketed all-reduces are graph nodes on the communication stream)
-        step.overlap_allreduce = True
+        # replayed from the captured halves of the step with the eager all-reduce between them (no collective lives
+        # inside a graph: ranks capture their per-bucket graphs at different steps)
+        step.overlap_allreduce = False
         graphed = GraphedTrainStep(step, global_frames=gf, global_positions=gp)
+        assert graphed.split
         pinned = (batch[0].pin_memory(), batch[1], batch[2].pin_memory(), batch[3], batch[4].pin_memory())
         graphed.run(pinned)
         graphed.run(pinned)

@@ -290,6 +290,8 @@ def rank_batch(args, rank, world, g, kind=None, mode=None, batch=None, sharded=F
 # algorithmic FLOPs per real squeezed frame (= packed row) of one launch of each GEMM family of the coupling net
 # (Modules.py:780-887): 2 * K * N; res_skip / b_rs are 192 x 384 for layers 0-2 and 192 x 192 for the last
 FAMILY_FLOPS_PER_ROW = {
+    # one WaveNet layer in one launch (flow_tc_layer.cuh): gate GEMM + res/skip GEMM
+    "layer": 2 * 960 * 384 + 2 * 192 * (3 * 384 + 192) / 4.0,
     "start": 2 * 80 * 192, "in_gate": 2 * 960 * 384, "res_skip": 2 * 192 * (3 * 384 + 192) / 4.0, "end": 2 * 192 * 160,
     "b_end": 2 * 160 * 192, "b_rs": 2 * (3 * 384 + 192) / 4.0 * 192, "b_in": 2 * 1920 * 192, "b_start": 2 * 192 * 80,
     # one block's weight gradients (wgrad_tc.cuh), one launch per shape class: the four k=5 gradients; end + 4 skip +
@@ -298,7 +300,7 @@ FAMILY_FLOPS_PER_ROW = {
 }
 # CTAs a launch of the family occupies (one CTA per SM: ~200 KB of shared memory each): (column slices per row tile, or a
 # fixed CTA count for the weight-gradient batches, which walk the whole row axis in 2 - 24 CTAs)
-FAMILY_SLICES = {"start": 1, "in_gate": 3, "res_skip": 2.5, "end": 1, "b_end": 1, "b_rs": 1, "b_in": 1, "b_start": 1}
+FAMILY_SLICES = {"layer": 1, "start": 1, "in_gate": 3, "res_skip": 2.5, "end": 1, "b_end": 1, "b_rs": 1, "b_in": 1, "b_start": 1}
 FAMILY_CTAS = {"wgrad_in": 24, "wgrad_1x1": 16, "wgrad_start": 2}
 
 
@@ -365,6 +367,11 @@ class TrainBench:
         self.barrier()
         e0.record()
         loss_host = None
+        # D2H read of every step's loss through pinned host memory, one step behind: step i's loss is copied out
+        # (stream-ordered) right after step i is issued and read on the host once step i + 1 has been issued, so the
+        # host never idles the GPU (what a training loop that logs its loss does); all reads are inside the timed region
+        host_loss = [torch.zeros(1).pin_memory() for _ in range(2)] if read_loss else None
+        host_ev = [torch.cuda.Event(), torch.cuda.Event()] if read_loss else None
         if prefetch and self.graphed is not None:
             self.graphed.prefetch(source[0])
         for i in range(steps):
@@ -372,7 +379,14 @@ class TrainBench:
             if prefetch and self.graphed is not None and i + 1 < steps:
                 self.graphed.prefetch(source[(i + 1) % len(source)])
             if read_loss:
-                loss_host = float(loss)                     # D2H read of the step's result
+                host_loss[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                host_ev[i & 1].record()
+                if i > 0:
+                    host_ev[(i - 1) & 1].synchronize()
+                    loss_host = float(host_loss[(i - 1) & 1])
+        if read_loss:
+            host_ev[(steps - 1) & 1].synchronize()
+            loss_host = float(host_loss[(steps - 1) & 1])             # the last step's loss, still before e1
         e1.record()
         self.barrier()
         launches = _lib.launch_count() - n0
@@ -539,6 +553,8 @@ def run_own(args):
         "padded_frames_per_sec": padded / (ms_per_step * args.steps * 1e-3),
         "e2e": {"value": e2e_frames / (e2e_ms * args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d + geo_bytes), "d2h_bytes_per_step": 4, "loss": loss_host,
+                "d2h": "every step's loss is copied to pinned host memory and read on the host one step later "
+                       "(after the next step has been issued); all reads inside the timed region",
                 "h2d": ("double-buffered: step i+1's batch is copied from pinned host memory while step i runs "
                         "(GraphedTrainStep.prefetch), every copy inside the timed region") if tb.graphed is not None
                        else "copied in front of every step"},

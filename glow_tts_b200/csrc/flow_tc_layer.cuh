@@ -16,13 +16,20 @@
 //     K-major layout the MMA reads -- it is the A operand of the second GEMM and never leaves the SM;
 //   * the res/skip GEMM runs from that slab through the same weight ring, TMEM ping-pong and epilogue warps.
 //
-// Same warp roles and barrier protocol as tc_gemm3_kernel: warps 0-3 stage h, warps 4 / 6 stream weight stages (one
-// cp.async.bulk each), warp 5 issues tcgen05.mma, warps 8-15 run the epilogues.  TMEM: two accumulators of
-// max(128, RS_BN) columns.
+// Same barrier protocol as tc_gemm3_kernel: warps 0-3 stage h, warps 4 / 6 stream weight stages (one cp.async.bulk
+// each), warp 5 issues tcgen05.mma.  The epilogues run on SIXTEEN warps (8-23; four per TMEM lane quarter, one
+// 32-column chunk of a 128-column slice each): with a CTA owning the whole layer of its row tile, the epilogue work of
+// a tile (~750 SASS instructions per thread and 32 columns: dropout hash, tanh / sigmoid, saved activations) is what
+// paces the kernel -- eight warps left it at 35 us per launch, no better than the two launches it replaces
+// (profiles/bench_r02l_*.json).  TMEM: two accumulators of max(128, RS_BN) columns.
 #pragma once
 #include "flow_tc.cuh"
 
 namespace glow {
+
+constexpr int kLayerEpiWarps = 16;                                    // warps 8 .. 23
+constexpr int kLayerThreads = (8 + kLayerEpiWarps) * 32;              // 768
+constexpr int kLayerStagingFloats = 32 * 17;                          // per epilogue warp: 32 rows x 16 columns, pitch 17
 
 // RS_N: output columns of the res/skip conv (384, or 192 for the last layer), RS_BN: its column slice per
 // accumulator, KS2: its K per weight stage -- (KS2 / 8) * RS_BN * 16 bytes must equal the gate's stage size.
@@ -38,7 +45,7 @@ struct LayerCfg {
     static constexpr int kStages = 3;
     static constexpr int kSub1 = kH / kTcKs, kSub2 = kH / KS2;   // weight stages per tap / per res-skip slice
     static constexpr int kSlices2 = RS_N / RS_BN;
-    static constexpr int kStagingBytes = kTcEpiWarps * kTcStagingFloats * 4;
+    static constexpr int kStagingBytes = kLayerEpiWarps * kLayerStagingFloats * 4;
     static constexpr int kSmemBytes = 2 * kPanelBytes + kStages * kStageBytes + kStagingBytes;   // h tile, acts slab, ring, staging
     static_assert(kSmemBytes <= kTcSmemCap, "layer kernel does not fit shared memory");
     static constexpr int kAccW = RS_BN > kGateBN ? RS_BN : kGateBN;
@@ -47,7 +54,7 @@ struct LayerCfg {
 };
 
 template <class Cfg, int RS_N, int RS_BN, int KS2, bool FAST>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kLayerThreads, 1)
 tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__restrict__ Wgate,
                 const __nv_bfloat16 *__restrict__ Wrs, const int32_t *__restrict__ row_utt, const int n_tiles,
                 const int rows_pad, const EpiGate<__nv_bfloat16, FAST> eg, const EpiResSkip<__nv_bfloat16> er)
@@ -66,8 +73,8 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
     float *sStage = reinterpret_cast<float *>(sB + S * Cfg::kStageBytes);
 
     if (tid == 0) {
-        mbar_init(&a_full, kTcLoaders); mbar_init(&a_empty, 1); mbar_init(&acts_full, kTcEpiWarps);
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps); }
+        mbar_init(&a_full, kTcLoaders); mbar_init(&a_empty, 1); mbar_init(&acts_full, kLayerEpiWarps);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLayerEpiWarps); }
         for (int i = 0; i < S; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_fence_init();
     }
@@ -167,11 +174,12 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                 }
             }
         }
-    } else if (warp >= 8) {                                            // ---- epilogue warps 8..15
-        const int q = warp & 3;                                        // TMEM lane quarter this warp may read
-        const int half = (warp >> 2) & 1;                              // even / odd 32-column chunks
-        float *stg = sStage + (warp - 8) * kTcStagingFloats;
-        const int sub_r = lane >> 2, sub_c = (lane & 3) * 8;           // transposed ownership: 8 rows x 4 column octets
+    } else if (warp >= 8) {                                            // ---- epilogue warps 8..23
+        const int e = warp - 8;
+        const int q = e & 3;                                           // TMEM lane quarter this warp may read (== warp % 4)
+        const int part = e >> 2;                                       // which 32-column chunk of a 128-column group
+        float *stg = sStage + e * kLayerStagingFloats;
+        const int sub_r = lane >> 1, sub_c = (lane & 1) * 8;           // transposed ownership: 16 rows x 2 column octets
         const uint32_t acts_smem = smem_u32(sActs);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -183,20 +191,21 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                 const uint32_t acc = it & 1u;
                 mbar_wait(&acc_full[acc], (it >> 1) & 1u);
                 tc_fence_after();
+                const int c0 = part * 32;
 #pragma unroll 1
-                for (int c0 = half * 32; c0 < Cfg::kGateBN; c0 += 64) {
+                for (int hh = 0; hh < 32; hh += 16) {
                     float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)c0, v);
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)(c0 + hh), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                    for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 2; ++i) {
                         float w[8], acts[4];
-                        const int rr = sub_r + 8 * i;
+                        const int rr = sub_r + 16 * i;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) w[j] = stg[rr * 33 + sub_c + j];
-                        const int n0 = s * Cfg::kGateBN + c0 + sub_c;                   // packed (tanh, sigmoid) column
+                        for (int j = 0; j < 8; ++j) w[j] = stg[rr * 17 + sub_c + j];
+                        const int n0 = s * Cfg::kGateBN + c0 + hh + sub_c;             // packed (tanh, sigmoid) column
                         eg.template apply_acts<8>(row_base + rr, __shfl_sync(0xffffffffu, my_utt, rr), n0, w, acts);
                         // acts channels n0/2 .. n0/2 + 3 of tile row q*32 + rr -> slab byte (ch/8)*pitch + row*16 + (ch%8)*2
                         const int ch = n0 >> 1;
@@ -220,21 +229,24 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                 mbar_wait(&acc_full[acc], (it >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = half * 32; c0 < RS_BN; c0 += 64) {
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)c0, v);
+                for (int c0 = part * 32; c0 < RS_BN; c0 += 128) {
+#pragma unroll 1
+                    for (int hh = 0; hh < 32; hh += 16) {
+                        float v[32];
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)(c0 + hh), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-                    __syncwarp();
+                        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
+                        __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float w[8];
-                        const int rr = sub_r + 8 * i;
+                        for (int i = 0; i < 2; ++i) {
+                            float w[8];
+                            const int rr = sub_r + 16 * i;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) w[j] = stg[rr * 33 + sub_c + j];
-                        er.template apply_u<8>(row_base + rr, __shfl_sync(0xffffffffu, my_utt, rr), s * RS_BN + c0 + sub_c, w);
+                            for (int j = 0; j < 8; ++j) w[j] = stg[rr * 17 + sub_c + j];
+                            er.template apply_u<8>(row_base + rr, __shfl_sync(0xffffffffu, my_utt, rr), s * RS_BN + c0 + hh + sub_c, w);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -264,7 +276,7 @@ int layer_tc(const __nv_bfloat16 *H, const __nv_bfloat16 *Wgate, const __nv_bflo
     const int n_tiles = rows_pad / 128;
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     ProfScope prof("layer", st);
-    kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(H, Wgate, Wrs, row_utt, n_tiles, rows_pad, eg, er);
+    kern<<<grid, kLayerThreads, Cfg::kSmemBytes, st>>>(H, Wgate, Wrs, row_utt, n_tiles, rows_pad, eg, er);
     GLOW_CHECK_LAUNCH("tc_layer_kernel");
     return GLOW_OK;
 }

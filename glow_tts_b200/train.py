@@ -251,6 +251,9 @@ class TrainStep:
         maps and the loss weights are then read from its device buffers, nothing from the host lists."""
         tokens, tl, mels, ml, spk = batch
         hp, model = self.hp, self.model
+        # the decoder's weight preparation (weight_norm -> slab images) only depends on the parameters: start it on
+        # the side stream before anything else of the step is queued (GlowTTS.forward finds it already running)
+        model.layer_Dict["Decoder"].begin_prepare(self.device)
         self.step_counter.add_(1)
         self.flat.zero_grad()
         # encoder weight gradients accumulate straight into the flat gradient buffer on the library's side stream

@@ -207,6 +207,14 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// ... and all the way into L1: the operands most epilogues combine with the accumulator (the residual stream, the
+// fp32 skip accumulator, the coupling input) were written by the previous launch and sit in L2; a dependent load right
+// before use costs the epilogue warps ~700 cycles each time (profiles/ncu_r02r_layer.md: long-scoreboard on exactly
+// those loads), a line prefetched while the MMAs run is an L1 hit.
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 // ============================================================== forward ========
 // Start 1x1 (Modules.py:791): h0 = (W y_a + b) * mask
@@ -287,9 +295,15 @@ struct EpiGate {
 // Res/skip 1x1 (Modules.py:871-881): h' = (h + res) * mask ; skip accumulates; last layer -> out * mask
 template <typename ActT>
 struct EpiResSkip {
-    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const float *bias; const ActT *Hin; ActT *Hout; float *SKIP; ActT *OUT; const int32_t *row_utt;
     int first, last;
+    // what apply_u adds to the accumulator for (row, 32 columns from n0): the residual input or the skip accumulator
+    __device__ __forceinline__ void prefetch32(int row, int n0) const
+    {
+        if (last) { if (!first) prefetch_l1(SKIP + (size_t)row * kH + n0); }
+        else if (n0 < kH) prefetch_l1(Hin + (size_t)row * kH + n0);
+        else if (!first) prefetch_l1(SKIP + (size_t)row * kH + (n0 - kH));
+    }
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         apply_u<NV>(row, row_utt[row], n0, v);
@@ -330,7 +344,12 @@ __device__ __forceinline__ int group_channel(int g, int i) { return (i >> 1) * k
 // coupling and then THIS block's 4x4 mix and ActNorm.
 template <typename ActT, bool FAST>
 struct EpiEnd {
-    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
+    // the coupling input of (row, packed columns n0 .. n0+31) = channels n0/2 .. n0/2+15 of both halves (64 B each)
+    __device__ __forceinline__ void prefetch32(int row, int n0) const
+    {
+        prefetch_l1(Y + (size_t)row * kC + (n0 >> 1));
+        prefetch_l1(Y + (size_t)row * kC + kCh + (n0 >> 1));
+    }
     const float *bias;          // [160] interleaved
     const float *Y;             // this block's input  [rows][160] (fwd: post-mix y ; rev: block output z)
     float *OUTS;                // [rows][160] interleaved (mean, logs), or null
@@ -447,8 +466,8 @@ struct EpiBwdGate {
     __device__ __forceinline__ void prefetch32(int row, int n0) const
     {
         const ActT *p = TS + (size_t)row * kG + 2 * n0;
-        prefetch_l2(p);
-        if (sizeof(ActT) == 4) prefetch_l2(p + 32);
+        prefetch_l1(p);
+        if (sizeof(ActT) == 4) prefetch_l1(p + 32);
     }
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
@@ -484,8 +503,11 @@ struct EpiBwdGate {
 // d(h_i) = conv^T(d pre) + d(h_{i+1}) (residual, Modules.py:878), masked
 template <typename ActT>
 struct EpiBwdIn {
-    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     const ActT *DHnext; ActT *DH; const int32_t *row_utt;
+    __device__ __forceinline__ void prefetch32(int row, int n0) const
+    {
+        if (DHnext != nullptr) prefetch_l1(DHnext + (size_t)row * kH + n0);
+    }
     template <int NV> __device__ __forceinline__ void apply(int row, int n0, const float *v) const
     {
         apply_u<NV>(row, row_utt[row], n0, v);
@@ -505,8 +527,8 @@ struct EpiBwdIn {
 
 // d(y_a) += d(h0) W_start
 struct EpiBwdStart {
-    __device__ __forceinline__ void prefetch32(int, int) const {}      // nothing to prefetch (see EpiBwdGate)
     float *DY;
+    __device__ __forceinline__ void prefetch32(int row, int n0) const { prefetch_l1(DY + (size_t)row * kC + n0); }
     template <int NV> __device__ __forceinline__ void apply_u(int row, int, int n0, const float *v) const
     {
         apply<NV>(row, n0, v);

@@ -226,6 +226,7 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
 #pragma unroll 1
             for (int s = 0; s < Cfg::kSlices2; ++s, ++it) {
                 const uint32_t acc = it & 1u;
+                for (int c0 = part * 32; c0 < RS_BN; c0 += 128) er.prefetch32(row_base + lane, s * RS_BN + c0);   // -> L1 while the MMAs run
                 mbar_wait(&acc_full[acc], (it >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll 1

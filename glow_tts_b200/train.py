@@ -531,8 +531,12 @@ class GraphedTrainStep:
         graph = torch.cuda.CUDAGraph()
         if self._pool is None:
             self._pool = torch.cuda.graph_pool_handle()         # replays are serialised: all graphs share one pool
-        # GLOW_GRAPH_PRIORITY=-1 captures on a high-priority stream (measured 0.13 ms/step slower at B = 32)
-        prio = int(os.environ.get("GLOW_GRAPH_PRIORITY", "0"))
+        # The step is captured on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were
+        # captured on, so the latency-bound main chain (decoder forward / data gradients, losses) gets free SMs before
+        # the encoder's stream and the weight-gradient lanes (default priority).  Round 1 measured this 0.13 ms slower
+        # (the library weight-gradient GEMMs it starved were needed on time); with the few-CTA background batches of
+        # round 2 it is 1 % faster (profiles/bench_r02u_graph_priority_*.json).  GLOW_GRAPH_PRIORITY=0: plain stream.
+        prio = int(os.environ.get("GLOW_GRAPH_PRIORITY", "-1"))
         cap = torch.cuda.Stream(dev, priority=prio) if prio != 0 else torch.cuda.Stream(dev)
         with _lib.capture_keepalive() as keep:
             with torch.cuda.graph(graph, pool=self._pool, stream=cap):

@@ -17,11 +17,37 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat16
 __device__ __forceinline__ void stf(float *p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16(v); }
 
+// ---- 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32 B sector per thread and instruction
+__device__ __forceinline__ void ld_global_256(const void *p, uint32_t (&r)[8])
+{
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ldg_global_256(const void *p, uint32_t (&r)[8])       // read-only data, non-coherent path
+{
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void *p, const uint32_t (&r)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 // ---- row-segment loads / stores: N consecutive elements starting at an address aligned to
 // N elements (the epilogues' column offsets are multiples of their NV), widest vector that fits.
+// Segments of 32 elements (the one-row-per-thread tcgen05 epilogues; 32-byte aligned there) go as 256-bit accesses.
 template <int N> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[N])
 {
-    if constexpr (N % 4 == 0) {
+    if constexpr (N % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i) {
+            uint32_t r[8];
+            ld_global_256(p + 8 * i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * i + j] = __uint_as_float(r[j]);
+        }
+    } else if constexpr (N % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < N / 4; ++i) {
             const float4 t = reinterpret_cast<const float4 *>(p)[i];
@@ -40,7 +66,15 @@ template <int N> __device__ __forceinline__ void ld_vec(const float *p, float (&
 }
 template <int N> __device__ __forceinline__ void st_vec(float *p, const float (&v)[N])
 {
-    if constexpr (N % 4 == 0) {
+    if constexpr (N % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[8 * i + j]);
+            st_global_256(p + 8 * i, r);
+        }
+    } else if constexpr (N % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < N / 4; ++i)
             reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -64,7 +98,15 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float &lo, float &hi)
 }
 template <int N> __device__ __forceinline__ void ld_vec(const __nv_bfloat16 *p, float (&v)[N])
 {
-    if constexpr (N % 8 == 0) {
+    if constexpr (N % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 16; ++i) {
+            uint32_t r[8];
+            ld_global_256(p + 16 * i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) unpack_bf16x2(r[j], v[16 * i + 2 * j], v[16 * i + 2 * j + 1]);
+        }
+    } else if constexpr (N % 8 == 0) {
 #pragma unroll
         for (int i = 0; i < N / 8; ++i) {
             const uint4 t = reinterpret_cast<const uint4 *>(p)[i];
@@ -87,7 +129,15 @@ template <int N> __device__ __forceinline__ void ld_vec(const __nv_bfloat16 *p, 
 }
 template <int N> __device__ __forceinline__ void st_vec(__nv_bfloat16 *p, const float (&v)[N])
 {
-    if constexpr (N % 8 == 0) {
+    if constexpr (N % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 16; ++i) {
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = pack_bf16x2(v[16 * i + 2 * j], v[16 * i + 2 * j + 1]);
+            st_global_256(p + 16 * i, r);
+        }
+    } else if constexpr (N % 8 == 0) {
 #pragma unroll
         for (int i = 0; i < N / 8; ++i)
             reinterpret_cast<uint4 *>(p)[i] =
@@ -111,20 +161,40 @@ template <int N> __device__ __forceinline__ void st_vec(__nv_bfloat16 *p, const 
 template <int N> __device__ __forceinline__ void ldg_vec(const __nv_bfloat16 *p, float (&v)[N])
 {
     static_assert(N % 8 == 0, "ldg_vec: multiples of 8");
+    if constexpr (N % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N / 8; ++i) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
-        unpack_bf16x2(t.x, v[8 * i], v[8 * i + 1]); unpack_bf16x2(t.y, v[8 * i + 2], v[8 * i + 3]);
-        unpack_bf16x2(t.z, v[8 * i + 4], v[8 * i + 5]); unpack_bf16x2(t.w, v[8 * i + 6], v[8 * i + 7]);
+        for (int i = 0; i < N / 16; ++i) {
+            uint32_t r[8];
+            ldg_global_256(p + 16 * i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) unpack_bf16x2(r[j], v[16 * i + 2 * j], v[16 * i + 2 * j + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 8; ++i) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            unpack_bf16x2(t.x, v[8 * i], v[8 * i + 1]); unpack_bf16x2(t.y, v[8 * i + 2], v[8 * i + 3]);
+            unpack_bf16x2(t.z, v[8 * i + 4], v[8 * i + 5]); unpack_bf16x2(t.w, v[8 * i + 6], v[8 * i + 7]);
+        }
     }
 }
 template <int N> __device__ __forceinline__ void ldg_vec(const float *p, float (&v)[N])
 {
     static_assert(N % 4 == 0, "ldg_vec: multiples of 4");
+    if constexpr (N % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N / 4; ++i) {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + i);
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        for (int i = 0; i < N / 8; ++i) {
+            uint32_t r[8];
+            ldg_global_256(p + 8 * i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * i + j] = __uint_as_float(r[j]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p) + i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
     }
 }
 
@@ -258,11 +328,18 @@ struct EpiGate {
     // memory as the A operand of the res/skip GEMM)
     template <int NV> __device__ __forceinline__ void apply_acts(int row, int utt, int n0, const float *v, float (&acts)[NV / 2]) const
     {
+        float b[NV];
+        ld_ro<NV>(bias + n0, b);
+        apply_acts_b<NV>(row, utt, n0, v, b, acts);
+    }
+    // the same with bias[n0 .. n0 + NV) supplied by the caller (flow_tc_layer.cuh keeps the bias vectors in shared memory)
+    template <int NV> __device__ __forceinline__ void apply_acts_b(int row, int utt, int n0, const float *v, const float *b,
+                                                                   float (&acts)[NV / 2]) const
+    {
         const bool m = utt >= 0;
         float pre[NV], ts[NV];
-        ld_ro<NV>(bias + n0, pre);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) pre[j] += v[j];
+        for (int j = 0; j < NV; ++j) pre[j] = b[j] + v[j];
         if (drop.seed != 0) {                                  // uniform over the launch
             const uint32_t t = drop.thresh(), s32 = drop.seed32(), i0 = drop.pair_index(row, n0);
             const float sc = drop.scale();
@@ -288,7 +365,14 @@ struct EpiGate {
             acts[j] = t * sg;
         }
         st_vec<NV>(TS + (size_t)row * kG + n0, ts);
-        st_vec<NV / 2>(ACTS + (size_t)row * kH + (n0 >> 1), acts);
+        if constexpr (NV == 32) {                              // 16 channels = one 32-byte sector
+            uint32_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = pack_bf16x2(acts[2 * j], acts[2 * j + 1]);
+            st_global_256(ACTS + (size_t)row * kH + (n0 >> 1), r);
+        } else {
+            st_vec<NV / 2>(ACTS + (size_t)row * kH + (n0 >> 1), acts);
+        }
     }
 };
 
@@ -311,26 +395,46 @@ struct EpiResSkip {
     // utt = row_utt[row], supplied by a caller that already holds it (tcgen05 epilogue: one load per row, shuffled)
     template <int NV> __device__ __forceinline__ void apply_u(int row, int utt, int n0, const float *v) const
     {
+        float old[NV];
+        load_old<NV>(row, n0, old);
+        apply_old<NV>(row, utt, n0, v, old);
+    }
+    // The two halves of apply_u: what is added to the accumulator (residual input or skip accumulator; owned by this
+    // thread alone, so it may be fetched long before the accumulator is ready -- flow_tc_layer.cuh does) ...
+    template <int NV> __device__ __forceinline__ void load_old(int row, int n0, float (&old)[NV]) const
+    {
         // n0 is a multiple of NV and NV divides kH, so the NV columns lie on one side of the res | skip split
-        const bool m = utt >= 0;
-        float b[NV], out[NV], old[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) old[j] = 0.f;
+        if (last) { if (!first) ld_vec<NV>(SKIP + (size_t)row * kH + n0, old); }
+        else if (n0 < kH) ld_ro<NV>(Hin + (size_t)row * kH + n0, old);
+        else if (!first) ld_vec<NV>(SKIP + (size_t)row * kH + (n0 - kH), old);
+    }
+    // ... and the arithmetic + store
+    template <int NV> __device__ __forceinline__ void apply_old(int row, int utt, int n0, const float *v, const float (&old)[NV]) const
+    {
+        float b[NV];
         ld_ro<NV>(bias + n0, b);
+        apply_old_b<NV>(row, utt, n0, v, old, b);
+    }
+    // ... with bias[n0 .. n0 + NV) supplied by the caller as well
+    template <int NV> __device__ __forceinline__ void apply_old_b(int row, int utt, int n0, const float *v, const float (&old)[NV],
+                                                                  const float *b) const
+    {
+        const bool m = utt >= 0;
+        float out[NV];
         if (last) {
-            if (!first) ld_vec<NV>(SKIP + (size_t)row * kH + n0, old);
 #pragma unroll
             for (int j = 0; j < NV; ++j) out[j] = m ? v[j] + b[j] + (first ? 0.f : old[j]) : 0.f;   // :881,:883
             st_vec<NV>(OUT + (size_t)row * kH + n0, out);
         } else if (n0 < kH) {
-            ld_ro<NV>(Hin + (size_t)row * kH + n0, old);
 #pragma unroll
             for (int j = 0; j < NV; ++j) out[j] = m ? old[j] + (v[j] + b[j]) : 0.f;                  // :878
             st_vec<NV>(Hout + (size_t)row * kH + n0, out);
         } else {
-            float *sk = SKIP + (size_t)row * kH + (n0 - kH);
-            if (!first) ld_vec<NV>(sk, old);
 #pragma unroll
             for (int j = 0; j < NV; ++j) out[j] = first ? v[j] + b[j] : old[j] + (v[j] + b[j]);      // :879
-            st_vec<NV>(sk, out);
+            st_vec<NV>(SKIP + (size_t)row * kH + (n0 - kH), out);
         }
     }
 };

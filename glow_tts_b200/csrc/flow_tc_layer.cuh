@@ -16,20 +16,30 @@
 //     K-major layout the MMA reads -- it is the A operand of the second GEMM and never leaves the SM;
 //   * the res/skip GEMM runs from that slab through the same weight ring, TMEM ping-pong and epilogue warps.
 //
-// Same barrier protocol as tc_gemm3_kernel: warps 0-3 stage h, warps 4 / 6 stream weight stages (one cp.async.bulk
-// each), warp 5 issues tcgen05.mma.  The epilogues run on SIXTEEN warps (8-23; four per TMEM lane quarter, one
-// 32-column chunk of a 128-column slice each): with a CTA owning the whole layer of its row tile, the epilogue work of
-// a tile (~750 SASS instructions per thread and 32 columns: dropout hash, tanh / sigmoid, saved activations) is what
-// paces the kernel -- eight warps left it at 35 us per launch, no better than the two launches it replaces
-// (profiles/bench_r02l_*.json).  TMEM: two accumulators of max(128, RS_BN) columns.
+// Same barrier protocol as tc_gemm3_kernel: warps 0-3 stage h (helped by the still idle epilogue warps for the CTA's
+// first tile), warps 4 / 6 stream weight stages (one cp.async.bulk each), warp 5 issues tcgen05.mma.  The epilogues
+// run on SIXTEEN warps (7-22; four per TMEM lane quarter, one 32-column chunk of a 128-column slice each).  A thread
+// owns one row: 32 accumulators come out of TMEM with one tcgen05.ld and leave as 256-bit global stores, the bias
+// vectors sit in shared memory, and what the res/skip epilogue adds (h, skip) is in registers before its accumulator
+// is ready.  TMEM: two accumulators of max(128, RS_BN) columns.
+//
+// Where the time of a CTA goes (GLOW_TC_DEBUG=1, cycles, one 128-row tile, profiles/layer_timeline_r02y.md):
+// h staged 3.7 k | gate GEMM 3 x 8 k | last gate epilogue 4-6 k | res/skip GEMM 3 k | res/skip epilogues 3 x 3-4 k.
+// The GEMMs run at ~135 cycles per 128x128x16 MMA against 64 of tensor time: each MMA reads 8 KB of operands from
+// shared memory and the weight ring takes another 4 KB of TMA writes per MMA -- 96 cycles of the 128 B/clk
+// shared-memory port -- and 80 CTAs stream the same 0.9 MB of weights out of L2 at once.  The cure for both is a
+// cta_group::2 pair sharing one weight stream (half the ring traffic and half the B operand per CTA) at N = 256;
+// that is the next step for this kernel and for the backward GEMMs.
 #pragma once
 #include "flow_tc.cuh"
 
 namespace glow {
 
-constexpr int kLayerEpiWarps = 16;                                    // warps 8 .. 23
-constexpr int kLayerThreads = (8 + kLayerEpiWarps) * 32;              // 768
-constexpr int kLayerStagingFloats = 32 * 17;                          // per epilogue warp: 32 rows x 16 columns, pitch 17
+constexpr int kLayerEpiWarp0 = 7;                                     // warps 0-3 load h, 4 / 6 stream weights, 5 issues MMAs
+constexpr int kLayerEpiWarps = 16;                                    // warps 7 .. 22
+constexpr int kLayerThreads = (kLayerEpiWarp0 + kLayerEpiWarps) * 32; // 736: leaves 88 registers per thread
+constexpr int kLayerFirstThreads = kTcLoaders + kLayerEpiWarps * 32;  // a CTA's first h tile: loaders + the still idle epilogue warps
+constexpr int kLayerFirstActive = 624;                                // = 24 * 26 rows per pass
 
 // RS_N: output columns of the res/skip conv (384, or 192 for the last layer), RS_BN: its column slice per
 // accumulator, KS2: its K per weight stage -- (KS2 / 8) * RS_BN * 16 bytes must equal the gate's stage size.
@@ -42,11 +52,10 @@ struct LayerCfg {
     static constexpr int kStageBytes = (kTcKs / 8) * kGateBN * 16;
     static_assert((KS2 / 8) * RS_BN * 16 == kStageBytes, "both GEMMs share one weight ring");
     static_assert(kH % KS2 == 0 && KS2 % 16 == 0 && RS_N % RS_BN == 0, "res/skip tiling");
-    static constexpr int kStages = 3;
+    static constexpr int kStages = 4;
     static constexpr int kSub1 = kH / kTcKs, kSub2 = kH / KS2;   // weight stages per tap / per res-skip slice
     static constexpr int kSlices2 = RS_N / RS_BN;
-    static constexpr int kStagingBytes = kLayerEpiWarps * kLayerStagingFloats * 4;
-    static constexpr int kSmemBytes = 2 * kPanelBytes + kStages * kStageBytes + kStagingBytes;   // h tile, acts slab, ring, staging
+    static constexpr int kSmemBytes = 2 * kPanelBytes + kStages * kStageBytes;                   // h tile, acts slab, ring
     static_assert(kSmemBytes <= kTcSmemCap, "layer kernel does not fit shared memory");
     static constexpr int kAccW = RS_BN > kGateBN ? RS_BN : kGateBN;
     static constexpr uint32_t kCols = 2 * kAccW <= 256 ? 256u : 512u;
@@ -57,23 +66,32 @@ template <class Cfg, int RS_N, int RS_BN, int KS2, bool FAST>
 __global__ void __launch_bounds__(kLayerThreads, 1)
 tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__restrict__ Wgate,
                 const __nv_bfloat16 *__restrict__ Wrs, const int32_t *__restrict__ row_utt, const int n_tiles,
-                const int rows_pad, const EpiGate<__nv_bfloat16, FAST> eg, const EpiResSkip<__nv_bfloat16> er)
+                const int rows_pad, const EpiGate<__nv_bfloat16, FAST> eg, const EpiResSkip<__nv_bfloat16> er,
+                long long *__restrict__ dbg_all)
 {
     using namespace sm100;
     constexpr int S = Cfg::kStages;
     constexpr int KPCH = Cfg::kKpch;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t a_full, a_empty, acts_full, b_full[4], b_empty[4], acc_full[2], acc_empty[2];
+    __shared__ uint64_t a_full, a_empty, a_first, acts_full, b_full[4], b_empty[4], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
+    // The bias vectors of both convs.  The epilogues read 8 of them per 8 outputs; from global memory that is a load the
+    // 40 KB of L1 left beside 210 KB of shared memory does not keep (the activations stream through it), i.e. an L2 round
+    // trip in front of every one of the 4 dependent rounds of a slice.
+    __shared__ __align__(16) float s_bgate[kG], s_brs[RS_N];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kG; i += kLayerThreads) s_bgate[i] = eg.bias[i];
+    for (int i = tid; i < RS_N; i += kLayerThreads) s_brs[i] = er.bias[i];
+    long long *dbg = (dbg_all != nullptr && blockIdx.x == gridDim.x / 2) ? dbg_all : nullptr;   // GLOW_TC_DEBUG timeline
+    if (dbg && tid == 0) dbg[0] = clock64();
     unsigned char *sA = smem;                                      // h tile (K-major slabs)
     unsigned char *sActs = smem + Cfg::kPanelBytes;                // acts tile, same layout (rows 0..127 used)
     unsigned char *sB = smem + 2 * Cfg::kPanelBytes;
-    float *sStage = reinterpret_cast<float *>(sB + S * Cfg::kStageBytes);
 
     if (tid == 0) {
         mbar_init(&a_full, kTcLoaders); mbar_init(&a_empty, 1); mbar_init(&acts_full, kLayerEpiWarps);
+        mbar_init(&a_first, kLayerFirstThreads);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kLayerEpiWarps); }
         for (int i = 0; i < S; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_fence_init();
@@ -83,13 +101,21 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (dbg && tid == 0) dbg[2] = clock64();
 
     if (warp < 4) {                                                    // ---- h loaders (128 threads)
         uint32_t n = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            if (n > 0) mbar_wait(&a_empty, (n - 1u) & 1u);
+            if (n == 0) {                                              // shared with the epilogue warps (below)
+                stage_panel<Cfg, kH, 0, kLayerFirstActive>(H, smem_u32(sA), tid, tile * 128 - kGuard, rows_pad, row_utt);
+                fence_proxy_async();                                   // generic-proxy writes -> tcgen05.mma reads
+                mbar_arrive(&a_first);
+                if (dbg && tid == 0) dbg[3] = clock64();
+                continue;
+            }
+            mbar_wait(&a_empty, (n - 1u) & 1u);
             stage_panel<Cfg, kH, 0, kTcLoadActive>(H, smem_u32(sA), tid, tile * 128 - kGuard, rows_pad, row_utt);
-            fence_proxy_async();                                       // generic-proxy writes -> tcgen05.mma reads
+            fence_proxy_async();
             mbar_arrive(&a_full);
         }
     } else if (warp == 4 || warp == 6) {
@@ -121,8 +147,9 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
             const uint32_t a_base = smem_u32(sA), acts_base = smem_u32(sActs), b_base = smem_u32(sB);
             uint32_t n = 0, slot = 0, bphase = 0, it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-                mbar_wait(&a_full, n & 1u);
+                if (n == 0) mbar_wait(&a_first, 0); else mbar_wait(&a_full, (n - 1u) & 1u);
                 tc_fence_after();
+                if (dbg && n == 0) dbg[4] = clock64();
                 // ---------------- gate GEMM: 3 column slices x 5 taps x K = 192
 #pragma unroll 1
                 for (int s = 0; s < Cfg::kGateSlices; ++s, ++it) {
@@ -148,10 +175,12 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                     }
                     if (s == Cfg::kGateSlices - 1) umma_commit(&a_empty);             // the h tile may be overwritten
                     umma_commit(&acc_full[acc]);
+                    if (dbg && n == 0) dbg[5 + s] = clock64();
                 }
                 // ---------------- res/skip GEMM from the acts slab the gate epilogue left in shared memory
                 mbar_wait(&acts_full, n & 1u);
                 tc_fence_after();
+                if (dbg && n == 0) dbg[8] = clock64();
 #pragma unroll 1
                 for (int s = 0; s < Cfg::kSlices2; ++s, ++it) {
                     const uint32_t acc = it & 1u;
@@ -171,53 +200,52 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                         if (++slot == S) { slot = 0; bphase ^= 1u; }
                     }
                     umma_commit(&acc_full[acc]);
+                    if (dbg && n == 0 && s < 3) dbg[9 + s] = clock64();
                 }
             }
         }
-    } else if (warp >= 8) {                                            // ---- epilogue warps 8..23
-        const int e = warp - 8;
-        const int q = e & 3;                                           // TMEM lane quarter this warp may read (== warp % 4)
+    } else if (warp >= kLayerEpiWarp0) {                               // ---- epilogue warps 7..22
+        // A thread owns ONE row (its TMEM lane) and 32 consecutive columns of a slice: accumulators come straight from
+        // tcgen05.ld into registers and leave as 256-bit global stores (a full 32 B sector per thread and instruction).
+        // No shared-memory transpose: shared-memory bandwidth is what this kernel runs out of (the MMAs read 8 KB of
+        // operands per instruction, TMA writes the weight ring), see DESIGN.md 5.
+        const int e = warp - kLayerEpiWarp0;
+        const int q = warp & 3;                                        // the TMEM lane quarter warp w may read is w % 4
         const int part = e >> 2;                                       // which 32-column chunk of a 128-column group
-        float *stg = sStage + e * kLayerStagingFloats;
-        const int sub_r = lane >> 1, sub_c = (lane & 1) * 8;           // transposed ownership: 16 rows x 2 column octets
         const uint32_t acts_smem = smem_u32(sActs);
+        if ((int)blockIdx.x < n_tiles) {                               // idle until the first accumulator: help stage the h tile
+            stage_panel<Cfg, kH, 0, kLayerFirstActive>(H, smem_u32(sA), tid - kLayerEpiWarp0 * 32 + kTcLoaders, blockIdx.x * 128 - kGuard, rows_pad, row_utt);
+            fence_proxy_async();
+            mbar_arrive(&a_first);
+        }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int row_base = tile * 128 + q * 32;
-            const int my_utt = row_utt[row_base + lane];
+            const int row = tile * 128 + q * 32 + lane;
+            const int my_utt = row_utt[row];
+            const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
             // ---------------- gate epilogue (+ acts into the shared-memory slab)
 #pragma unroll 1
             for (int s = 0; s < Cfg::kGateSlices; ++s, ++it) {
                 const uint32_t acc = it & 1u;
                 mbar_wait(&acc_full[acc], (it >> 1) & 1u);
                 tc_fence_after();
-                const int c0 = part * 32;
-#pragma unroll 1
-                for (int hh = 0; hh < 32; hh += 16) {
-                    float v[32];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)(c0 + hh), v);
+                const bool mark = dbg && e == 0 && lane == 0 && tile == (int)blockIdx.x;
+                if (mark) dbg[12 + s] = clock64();
+                const int n0 = s * Cfg::kGateBN + part * 32;           // packed (tanh, sigmoid) columns n0 .. n0 + 31
+                float v[32], acts[16];
+                tmem_ld32(lane_addr + acc * Cfg::kAccW + (uint32_t)(part * 32), v);
+                eg.template apply_acts_b<32>(row, my_utt, n0, v, s_bgate + n0, acts);
+                // acts channels n0/2 .. n0/2 + 15 of tile row q*32 + lane -> slab byte (ch/8)*pitch + row*16 + (ch%8)*2
+                const uint32_t dst = acts_smem + (uint32_t)(n0 >> 4) * kTcPitch + (uint32_t)(q * 32 + lane) * 16u;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        float w[8], acts[4];
-                        const int rr = sub_r + 16 * i;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) w[j] = stg[rr * 17 + sub_c + j];
-                        const int n0 = s * Cfg::kGateBN + c0 + hh + sub_c;             // packed (tanh, sigmoid) column
-                        eg.template apply_acts<8>(row_base + rr, __shfl_sync(0xffffffffu, my_utt, rr), n0, w, acts);
-                        // acts channels n0/2 .. n0/2 + 3 of tile row q*32 + rr -> slab byte (ch/8)*pitch + row*16 + (ch%8)*2
-                        const int ch = n0 >> 1;
-                        const uint32_t dst = acts_smem + (uint32_t)(ch >> 3) * kTcPitch + (uint32_t)(q * 32 + rr) * 16u + (uint32_t)(ch & 7) * 2u;
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(pack_bf16x2(acts[0], acts[1])),
-                                     "r"(pack_bf16x2(acts[2], acts[3])) : "memory");
-                    }
-                    __syncwarp();
-                }
+                for (int c = 0; c < 2; ++c)
+                    st_shared16(dst + (uint32_t)c * kTcPitch,
+                                make_uint4(pack_bf16x2(acts[8 * c], acts[8 * c + 1]), pack_bf16x2(acts[8 * c + 2], acts[8 * c + 3]),
+                                           pack_bf16x2(acts[8 * c + 4], acts[8 * c + 5]), pack_bf16x2(acts[8 * c + 6], acts[8 * c + 7])));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (mark) dbg[15 + s] = clock64();
             }
             fence_proxy_async();                                       // the acts slab: generic-proxy stores -> tcgen05.mma reads
             __syncwarp();
@@ -226,37 +254,32 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
 #pragma unroll 1
             for (int s = 0; s < Cfg::kSlices2; ++s, ++it) {
                 const uint32_t acc = it & 1u;
-                for (int c0 = part * 32; c0 < RS_BN; c0 += 128) er.prefetch32(row_base + lane, s * RS_BN + c0);   // -> L1 while the MMAs run
+                // what the epilogue adds to the accumulators (h or skip: this thread's own elements) is fetched into
+                // registers BEFORE the wait, while the MMAs run
+                float old[32];
+                er.template load_old<32>(row, s * RS_BN + part * 32, old);
                 mbar_wait(&acc_full[acc], (it >> 1) & 1u);
                 tc_fence_after();
+                const bool mark = dbg && e == 0 && lane == 0 && tile == (int)blockIdx.x && s < 3;
+                if (mark) dbg[18 + s] = clock64();
 #pragma unroll 1
                 for (int c0 = part * 32; c0 < RS_BN; c0 += 128) {
-#pragma unroll 1
-                    for (int hh = 0; hh < 32; hh += 16) {
-                        float v[32];
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccW + (uint32_t)(c0 + hh), v);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = v[j];
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float w[8];
-                            const int rr = sub_r + 16 * i;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) w[j] = stg[rr * 17 + sub_c + j];
-                            er.template apply_u<8>(row_base + rr, __shfl_sync(0xffffffffu, my_utt, rr), s * RS_BN + c0 + hh + sub_c, w);
-                        }
-                        __syncwarp();
-                    }
+                    const int n0 = s * RS_BN + c0;
+                    float v[32];
+                    tmem_ld32(lane_addr + acc * Cfg::kAccW + (uint32_t)c0, v);
+                    if (RS_BN > 128 && c0 != part * 32) er.template load_old<32>(row, n0, old);
+                    er.template apply_old_b<32>(row, my_utt, n0, v, old, s_brs + n0);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (mark) dbg[21 + s] = clock64();
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (dbg && tid == 0) dbg[1] = clock64();
     if (warp == 5) tmem_dealloc(tmem, Cfg::kCols);
 }
 
@@ -276,9 +299,32 @@ int layer_tc(const __nv_bfloat16 *H, const __nv_bfloat16 *Wgate, const __nv_bflo
     }
     const int n_tiles = rows_pad / 128;
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    ProfScope prof("layer", st);
-    kern<<<grid, kLayerThreads, Cfg::kSmemBytes, st>>>(H, Wgate, Wrs, row_utt, n_tiles, rows_pad, eg, er);
-    GLOW_CHECK_LAUNCH("tc_layer_kernel");
+    // GLOW_TC_DEBUG=1: timeline of the middle CTA for 3 launches, after GLOW_TC_DEBUG_SKIP launches (a warm step)
+    static int dbg_left = getenv("GLOW_TC_DEBUG") ? 3 : 0;
+    static int dbg_skip = getenv("GLOW_TC_DEBUG_SKIP") ? atoi(getenv("GLOW_TC_DEBUG_SKIP")) : 0;
+    static long long *dbg_buf = nullptr;
+    const bool dbg_on = dbg_left > 0 && dbg_skip-- <= 0;
+    if (dbg_on) {
+        if (!dbg_buf) GLOW_CHECK_CUDA(cudaMalloc(&dbg_buf, 32 * sizeof(long long)));
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 32 * sizeof(long long), st));
+        --dbg_left;
+    }
+    {
+        ProfScope prof("layer", st);
+        kern<<<grid, kLayerThreads, Cfg::kSmemBytes, st>>>(H, Wgate, Wrs, row_utt, n_tiles, rows_pad, eg, er,
+                                                           dbg_on ? dbg_buf : nullptr);
+        GLOW_CHECK_LAUNCH("tc_layer_kernel");
+    }
+    if (dbg_on) {
+        long long h[32];
+        GLOW_CHECK_CUDA(cudaStreamSynchronize(st));
+        GLOW_CHECK_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        auto t = [&](int i) { return h[i] ? h[i] - h[0] : -1LL; };
+        fprintf(stderr, "[tc-debug] layer<%d> grid=%d | setup=%lld h_staged=%lld a_full=%lld end=%lld\n", RS_N, grid, t(2), t(3), t(4), t(1));
+        fprintf(stderr, "[tc-debug]   gate issued %lld %lld %lld | acts_full=%lld | rs issued %lld %lld %lld\n", t(5), t(6), t(7), t(8), t(9), t(10), t(11));
+        fprintf(stderr, "[tc-debug]   E1 acc_full %lld %lld %lld done %lld %lld %lld | E2 acc_full %lld %lld %lld done %lld %lld %lld\n",
+                t(12), t(13), t(14), t(15), t(16), t(17), t(18), t(19), t(20), t(21), t(22), t(23));
+    }
     return GLOW_OK;
 }
 

@@ -13,5 +13,6 @@ for blk in model.layer_Dict["Decoder"].layer_Dict["Flows"]:
 model = model.cuda().train()
 step = TrainStep(model, hp, torch.device("cuda:0"))
 b = step.to_device(bench.workload_batch("lj", 32, 0))
-step.run(b)
+for _ in range(int(os.environ.get("GLOW_TC_DEBUG_STEPS", "1"))):
+    step.run(b)
 torch.cuda.synchronize()

@@ -118,90 +118,133 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
             fence_proxy_async();
             mbar_arrive(&a_full);
         }
-    } else if (warp == 4 || warp == 6) {
-        if (lane == 0) {                                               // ---- weight producers
-            const uint32_t which = (warp == 4) ? 0u : 1u;
-            uint32_t bc = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    } else if (warp == 4 || warp == 6) {                               // ---- weight producers (converged warp, elected lane issues)
+        const uint32_t which = (warp == 4) ? 0u : 1u;
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]), ring0 = smem_u32(sB);
+        uint32_t bc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
-                for (int q = 0; q < Cfg::kStagesPerItem; ++q, ++bc) {
-                    if ((bc & 1u) != which) continue;
-                    const __nv_bfloat16 *src;
-                    if (q < Cfg::kGateSlices * kTaps * Cfg::kSub1) {    // gate: (slice, tap, st)
-                        src = Wgate + (size_t)(q / Cfg::kSub1) * KPCH * Cfg::kGateBN * 8 +
-                              (size_t)(q % Cfg::kSub1) * (kTcKs / 8) * Cfg::kGateBN * 8;
-                    } else {                                            // res/skip: (slice, st)
-                        const int r = q - Cfg::kGateSlices * kTaps * Cfg::kSub1;
-                        src = Wrs + (size_t)(r / Cfg::kSub2) * KPCH * RS_BN * 8 + (size_t)(r % Cfg::kSub2) * (KS2 / 8) * RS_BN * 8;
-                    }
-                    const uint32_t slot = bc % S, round = bc / S;
-                    if (round > 0) mbar_wait(&b_empty[slot], (round - 1u) & 1u);
-                    mbar_arrive_expect_tx(&b_full[slot], Cfg::kStageBytes);
-                    bulk_g2s(sB + (size_t)slot * Cfg::kStageBytes, src, Cfg::kStageBytes, &b_full[slot]);
+            for (int q = 0; q < Cfg::kStagesPerItem; ++q, ++bc) {
+                if ((bc & 1u) != which) continue;
+                const __nv_bfloat16 *src;
+                if (q < Cfg::kGateSlices * kTaps * Cfg::kSub1) {        // gate: (slice, tap, st)
+                    src = Wgate + (size_t)(q / Cfg::kSub1) * KPCH * Cfg::kGateBN * 8 +
+                          (size_t)(q % Cfg::kSub1) * (kTcKs / 8) * Cfg::kGateBN * 8;
+                } else {                                                // res/skip: (slice, st)
+                    const int r = q - Cfg::kGateSlices * kTaps * Cfg::kSub1;
+                    src = Wrs + (size_t)(r / Cfg::kSub2) * KPCH * RS_BN * 8 + (size_t)(r % Cfg::kSub2) * (KS2 / 8) * RS_BN * 8;
                 }
+                const uint32_t slot = bc % S, round = bc / S;
+                if (round > 0) mbar_wait_a(bempty0 + slot * 8u, (round - 1u) & 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx_a(bfull0 + slot * 8u, Cfg::kStageBytes);
+                    bulk_g2s_a(ring0 + slot * Cfg::kStageBytes, src, Cfg::kStageBytes, bfull0 + slot * 8u);
+                    if (dbg && bc < 36) dbg[32 + bc] = clock64();         // stage bc issued
+                }
+                __syncwarp();
             }
         }
-    } else if (warp == 5) {
-        if (lane == 0) {                                               // ---- MMA issuer
-            constexpr uint32_t idesc1 = idesc_bf16_f32(128, Cfg::kGateBN), idesc2 = idesc_bf16_f32(128, RS_BN);
-            const uint32_t a_base = smem_u32(sA), acts_base = smem_u32(sActs), b_base = smem_u32(sB);
-            uint32_t n = 0, slot = 0, bphase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-                if (n == 0) mbar_wait(&a_first, 0); else mbar_wait(&a_full, (n - 1u) & 1u);
-                tc_fence_after();
-                if (dbg && n == 0) dbg[4] = clock64();
-                // ---------------- gate GEMM: 3 column slices x 5 taps x K = 192
+    } else if (warp == 5) {                                            // ---- MMA issuer (converged warp, elected lane issues)
+        constexpr uint32_t idesc1 = idesc_bf16_f32(128, Cfg::kGateBN), idesc2 = idesc_bf16_f32(128, RS_BN);
+        // everything the per-stage loop needs, computed once: barrier addresses and the descriptors of slot 0 (a
+        // descriptor's address field counts 16 B units, so slot s is + s * stage bytes / 16)
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]);
+        const uint32_t accfull0 = smem_u32(&acc_full[0]), accempty0 = smem_u32(&acc_empty[0]);
+        const uint64_t ad_h = smem_desc(smem_u32(sA), kTcPitch, 128), ad_acts = smem_desc(smem_u32(sActs), kTcPitch, 128);
+        const uint64_t bd_gate0 = smem_desc(smem_u32(sB), Cfg::kGateBN * 16u, 128), bd_rs0 = smem_desc(smem_u32(sB), RS_BN * 16u, 128);
+        uint32_t n = 0, slot = 0, bphase = 0, it = 0;
+        // whether the NEXT weight stage is already known to have landed: each stage probes its successor's barrier
+        // between its own MMAs (a successful mbarrier.try_wait is ~140 cycles on this thread; behind the MMAs in flight it is free)
+        bool have = false;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            if (n == 0) mbar_wait(&a_first, 0); else mbar_wait(&a_full, (n - 1u) & 1u);
+            tc_fence_after();
+            if (dbg && n == 0 && lane == 0) dbg[4] = clock64();
+            // ---------------- gate GEMM: 3 column slices x 5 taps x K = 192
 #pragma unroll 1
-                for (int s = 0; s < Cfg::kGateSlices; ++s, ++it) {
-                    const uint32_t acc = it & 1u;
-                    if (it >= 2) { mbar_wait(&acc_empty[acc], ((it >> 1) - 1u) & 1u); tc_fence_after(); }
-                    const uint32_t d_tmem = tmem + acc * Cfg::kAccW;
-                    uint64_t a_tap = smem_desc(a_base, kTcPitch, 128);               // tap t reads staged rows t .. t + 127
+            for (int s = 0; s < Cfg::kGateSlices; ++s, ++it) {
+                const uint32_t acc = it & 1u;
+                if (it >= 2) { mbar_wait_a(accempty0 + acc * 8u, ((it >> 1) - 1u) & 1u); tc_fence_after(); }
+                const uint32_t d_tmem = tmem + acc * Cfg::kAccW;
+                uint64_t a_tap = ad_h;                                           // tap t reads staged rows t .. t + 127
 #pragma unroll 1
-                    for (int tap = 0; tap < kTaps; ++tap, a_tap += 1) {
+                for (int tap = 0; tap < kTaps; ++tap, a_tap += 1) {
 #pragma unroll 1
-                        for (int st = 0; st < Cfg::kSub1; ++st) {
-                            mbar_wait(&b_full[slot], bphase);
-                            tc_fence_after();
-                            const uint64_t ad = a_tap + (uint64_t)(st * (kTcKs / 8) * (kTcPitch / 16));
-                            const uint64_t bd = smem_desc(b_base + slot * Cfg::kStageBytes, Cfg::kGateBN * 16u, 128);
+                    for (int st = 0; st < Cfg::kSub1; ++st) {
+                        const int sq = (s * kTaps + tap) * Cfg::kSub1 + st;   // stage index within the tile
+                        if (dbg && n == 0 && sq < 36 && lane == 0) dbg[68 + sq] = clock64();
+                        if (!have) mbar_wait_a(bfull0 + slot * 8u, bphase);
+                        tc_fence_after();
+                        if (dbg && n == 0 && sq < 36 && lane == 0) dbg[104 + sq] = clock64();
+                        const uint32_t nslot = slot + 1 == S ? 0u : slot + 1, nphase = slot + 1 == S ? bphase ^ 1u : bphase;
+                        const uint64_t ad = a_tap + (uint64_t)(st * (kTcKs / 8) * (kTcPitch / 16));
+                        const uint64_t bd = bd_gate0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
+                        constexpr int kJ = kTcKs / 16, kJ0 = kJ - 2;      // MMAs per stage; the last two go behind the probe
+                        if (elect_one()) {
 #pragma unroll
-                            for (int j = 0; j < kTcKs / 16; ++j)
+                            for (int j = 0; j < kJ0; ++j)
                                 umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * Cfg::kGateBN),
                                           idesc1, (tap | st | j) != 0);
-                            umma_commit(&b_empty[slot]);
-                            if (++slot == S) { slot = 0; bphase ^= 1u; }
                         }
-                    }
-                    if (s == Cfg::kGateSlices - 1) umma_commit(&a_empty);             // the h tile may be overwritten
-                    umma_commit(&acc_full[acc]);
-                    if (dbg && n == 0) dbg[5 + s] = clock64();
-                }
-                // ---------------- res/skip GEMM from the acts slab the gate epilogue left in shared memory
-                mbar_wait(&acts_full, n & 1u);
-                tc_fence_after();
-                if (dbg && n == 0) dbg[8] = clock64();
-#pragma unroll 1
-                for (int s = 0; s < Cfg::kSlices2; ++s, ++it) {
-                    const uint32_t acc = it & 1u;
-                    if (it >= 2) { mbar_wait(&acc_empty[acc], ((it >> 1) - 1u) & 1u); tc_fence_after(); }
-                    const uint32_t d_tmem = tmem + acc * Cfg::kAccW;
-#pragma unroll 1
-                    for (int st = 0; st < Cfg::kSub2; ++st) {
-                        mbar_wait(&b_full[slot], bphase);
-                        tc_fence_after();
-                        const uint64_t ad = smem_desc(acts_base, kTcPitch, 128) + (uint64_t)(st * (KS2 / 8) * (kTcPitch / 16));
-                        const uint64_t bd = smem_desc(b_base + slot * Cfg::kStageBytes, RS_BN * 16u, 128);
+                        __syncwarp();
+                        have = mbar_try_wait_a(bfull0 + nslot * 8u, nphase);      // ~140 cycles, hidden behind the MMAs in flight
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < KS2 / 16; ++j)
-                            umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * RS_BN), idesc2,
-                                      (st | j) != 0);
-                        umma_commit(&b_empty[slot]);
+                            for (int j = kJ0; j < kJ; ++j)
+                                umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * Cfg::kGateBN),
+                                          idesc1, true);
+                            umma_commit_a(bempty0 + slot * 8u);
+                        }
+                        __syncwarp();
                         if (++slot == S) { slot = 0; bphase ^= 1u; }
                     }
-                    umma_commit(&acc_full[acc]);
+                }
+                if (elect_one()) {
+                    if (s == Cfg::kGateSlices - 1) umma_commit(&a_empty);             // the h tile may be overwritten
+                    umma_commit_a(accfull0 + acc * 8u);
+                    if (dbg && n == 0) dbg[5 + s] = clock64();
+                }
+                __syncwarp();
+            }
+            // ---------------- res/skip GEMM from the acts slab the gate epilogue left in shared memory
+            mbar_wait(&acts_full, n & 1u);
+            tc_fence_after();
+            if (dbg && n == 0 && lane == 0) dbg[8] = clock64();
+#pragma unroll 1
+            for (int s = 0; s < Cfg::kSlices2; ++s, ++it) {
+                const uint32_t acc = it & 1u;
+                if (it >= 2) { mbar_wait_a(accempty0 + acc * 8u, ((it >> 1) - 1u) & 1u); tc_fence_after(); }
+                const uint32_t d_tmem = tmem + acc * Cfg::kAccW;
+#pragma unroll 1
+                for (int st = 0; st < Cfg::kSub2; ++st) {
+                    if (!have) mbar_wait_a(bfull0 + slot * 8u, bphase);
+                    tc_fence_after();
+                    const uint32_t nslot = slot + 1 == S ? 0u : slot + 1, nphase = slot + 1 == S ? bphase ^ 1u : bphase;
+                    const uint64_t ad = ad_acts + (uint64_t)(st * (KS2 / 8) * (kTcPitch / 16));
+                    const uint64_t bd = bd_rs0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
+                    constexpr int kJ = KS2 / 16, kJ0 = kJ - 2;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < kJ0; ++j)
+                            umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * RS_BN), idesc2,
+                                      (st | j) != 0);
+                    }
+                    __syncwarp();
+                    have = mbar_try_wait_a(bfull0 + nslot * 8u, nphase);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = kJ0; j < kJ; ++j)
+                            umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * RS_BN), idesc2, true);
+                        umma_commit_a(bempty0 + slot * 8u);
+                    }
+                    __syncwarp();
+                    if (++slot == S) { slot = 0; bphase ^= 1u; }
+                }
+                if (elect_one()) {
+                    umma_commit_a(accfull0 + acc * 8u);
                     if (dbg && n == 0 && s < 3) dbg[9 + s] = clock64();
                 }
+                __syncwarp();
             }
         }
     } else if (warp >= kLayerEpiWarp0) {                               // ---- epilogue warps 7..22
@@ -305,8 +348,8 @@ int layer_tc(const __nv_bfloat16 *H, const __nv_bfloat16 *Wgate, const __nv_bflo
     static long long *dbg_buf = nullptr;
     const bool dbg_on = dbg_left > 0 && dbg_skip-- <= 0;
     if (dbg_on) {
-        if (!dbg_buf) GLOW_CHECK_CUDA(cudaMalloc(&dbg_buf, 32 * sizeof(long long)));
-        GLOW_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 32 * sizeof(long long), st));
+        if (!dbg_buf) GLOW_CHECK_CUDA(cudaMalloc(&dbg_buf, 160 * sizeof(long long)));
+        GLOW_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, 160 * sizeof(long long), st));
         --dbg_left;
     }
     {
@@ -316,7 +359,7 @@ int layer_tc(const __nv_bfloat16 *H, const __nv_bfloat16 *Wgate, const __nv_bflo
         GLOW_CHECK_LAUNCH("tc_layer_kernel");
     }
     if (dbg_on) {
-        long long h[32];
+        long long h[160];
         GLOW_CHECK_CUDA(cudaStreamSynchronize(st));
         GLOW_CHECK_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
         auto t = [&](int i) { return h[i] ? h[i] - h[0] : -1LL; };
@@ -324,6 +367,9 @@ int layer_tc(const __nv_bfloat16 *H, const __nv_bfloat16 *Wgate, const __nv_bflo
         fprintf(stderr, "[tc-debug]   gate issued %lld %lld %lld | acts_full=%lld | rs issued %lld %lld %lld\n", t(5), t(6), t(7), t(8), t(9), t(10), t(11));
         fprintf(stderr, "[tc-debug]   E1 acc_full %lld %lld %lld done %lld %lld %lld | E2 acc_full %lld %lld %lld done %lld %lld %lld\n",
                 t(12), t(13), t(14), t(15), t(16), t(17), t(18), t(19), t(20), t(21), t(22), t(23));
+        fprintf(stderr, "[tc-debug]   weight stages (issued by the producer / MMA thread starts waiting / sees the stage):");
+        for (int i = 0; i < 36; ++i) fprintf(stderr, "%s %lld/%lld/%lld", i % 6 == 0 ? "\n[tc-debug]    " : " |", t(32 + i), t(68 + i), t(104 + i));
+        fprintf(stderr, "\n");
     }
     return GLOW_OK;
 }

@@ -43,6 +43,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  The single-thread roles (tcgen05.mma issue, bulk
+// copies) are written as "the whole warp walks the pipeline, the elected lane issues": behind elect.sync the compiler
+// keeps descriptors and barrier addresses in uniform registers and emits UTCHMMA / UBLKCP back to back, while behind
+// `if (lane == 0)` it cannot prove a single active lane and wraps EVERY such instruction in an ELECT / R2UR /
+// BRA.U.ANY loop -- ~70 issue cycles per MMA and ~200 per pipeline stage on a thread that has 64 cycles per MMA
+// (profiles/layer_timeline_r02y.md).  The same lane is elected every time for the same member mask.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// The *_a forms take a shared-window address computed ONCE (smem_u32 outside the loop): taking `&bar[slot]` of a
+// __shared__ array inside a pipeline loop costs an S2UR SR_CgaCtaId + address arithmetic per use, which is on the
+// critical path of the thread that feeds the tensor pipe.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+        if (mbar_try_wait_a(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -128,6 +168,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accum)
         : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // All previously issued MMAs of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).

@@ -153,9 +153,9 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
         const uint64_t ad_h = smem_desc(smem_u32(sA), kTcPitch, 128), ad_acts = smem_desc(smem_u32(sActs), kTcPitch, 128);
         const uint64_t bd_gate0 = smem_desc(smem_u32(sB), Cfg::kGateBN * 16u, 128), bd_rs0 = smem_desc(smem_u32(sB), RS_BN * 16u, 128);
         uint32_t n = 0, slot = 0, bphase = 0, it = 0;
-        // whether the NEXT weight stage is already known to have landed: each stage probes its successor's barrier
-        // between its own MMAs (a successful mbarrier.try_wait is ~140 cycles on this thread; behind the MMAs in flight it is free)
-        bool have = false;
+        // (probing the NEXT stage's barrier between the MMAs of the current one hides the ~140 cycles a successful
+        // mbarrier.try_wait costs this thread -- stage period 558 -> 510 cycles in the first slice -- but the launch got
+        // 1.3 us slower in the graph: later slices wait for weights that the epilogue's stores delay in L2, not for this thread)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
             if (n == 0) mbar_wait(&a_first, 0); else mbar_wait(&a_full, (n - 1u) & 1u);
             tc_fence_after();
@@ -173,26 +173,16 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                     for (int st = 0; st < Cfg::kSub1; ++st) {
                         const int sq = (s * kTaps + tap) * Cfg::kSub1 + st;   // stage index within the tile
                         if (dbg && n == 0 && sq < 36 && lane == 0) dbg[68 + sq] = clock64();
-                        if (!have) mbar_wait_a(bfull0 + slot * 8u, bphase);
+                        mbar_wait_a(bfull0 + slot * 8u, bphase);
                         tc_fence_after();
                         if (dbg && n == 0 && sq < 36 && lane == 0) dbg[104 + sq] = clock64();
-                        const uint32_t nslot = slot + 1 == S ? 0u : slot + 1, nphase = slot + 1 == S ? bphase ^ 1u : bphase;
-                        const uint64_t ad = a_tap + (uint64_t)(st * (kTcKs / 8) * (kTcPitch / 16));
-                        const uint64_t bd = bd_gate0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
-                        constexpr int kJ = kTcKs / 16, kJ0 = kJ - 2;      // MMAs per stage; the last two go behind the probe
                         if (elect_one()) {
+                            const uint64_t ad = a_tap + (uint64_t)(st * (kTcKs / 8) * (kTcPitch / 16));
+                            const uint64_t bd = bd_gate0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
 #pragma unroll
-                            for (int j = 0; j < kJ0; ++j)
+                            for (int j = 0; j < kTcKs / 16; ++j)
                                 umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * Cfg::kGateBN),
                                           idesc1, (tap | st | j) != 0);
-                        }
-                        __syncwarp();
-                        have = mbar_try_wait_a(bfull0 + nslot * 8u, nphase);      // ~140 cycles, hidden behind the MMAs in flight
-                        if (elect_one()) {
-#pragma unroll
-                            for (int j = kJ0; j < kJ; ++j)
-                                umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * Cfg::kGateBN),
-                                          idesc1, true);
                             umma_commit_a(bempty0 + slot * 8u);
                         }
                         __syncwarp();
@@ -217,24 +207,15 @@ tc_layer_kernel(const __nv_bfloat16 *__restrict__ H, const __nv_bfloat16 *__rest
                 const uint32_t d_tmem = tmem + acc * Cfg::kAccW;
 #pragma unroll 1
                 for (int st = 0; st < Cfg::kSub2; ++st) {
-                    if (!have) mbar_wait_a(bfull0 + slot * 8u, bphase);
+                    mbar_wait_a(bfull0 + slot * 8u, bphase);
                     tc_fence_after();
-                    const uint32_t nslot = slot + 1 == S ? 0u : slot + 1, nphase = slot + 1 == S ? bphase ^ 1u : bphase;
-                    const uint64_t ad = ad_acts + (uint64_t)(st * (KS2 / 8) * (kTcPitch / 16));
-                    const uint64_t bd = bd_rs0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
-                    constexpr int kJ = KS2 / 16, kJ0 = kJ - 2;
                     if (elect_one()) {
+                        const uint64_t ad = ad_acts + (uint64_t)(st * (KS2 / 8) * (kTcPitch / 16));
+                        const uint64_t bd = bd_rs0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
 #pragma unroll
-                        for (int j = 0; j < kJ0; ++j)
+                        for (int j = 0; j < KS2 / 16; ++j)
                             umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * RS_BN), idesc2,
                                       (st | j) != 0);
-                    }
-                    __syncwarp();
-                    have = mbar_try_wait_a(bfull0 + nslot * 8u, nphase);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int j = kJ0; j < kJ; ++j)
-                            umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * RS_BN), idesc2, true);
                         umma_commit_a(bempty0 + slot * 8u);
                     }
                     __syncwarp();

@@ -250,70 +250,80 @@ tc_gemm3_kernel(const TcA a, const __nv_bfloat16 *__restrict__ Wslab, const int3
                 mbar_arrive(&a_full[buf]);
             }
         }
-    } else if (warp == 4 || warp == 6) {
-        if (lane == 0) {                                               // ---- weight producers
-            const uint32_t which = (warp == 4) ? 0u : 1u;
-            uint32_t bc = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int slice = item % NSL;
+    } else if (warp == 4 || warp == 6) {                               // ---- weight producers (converged warp, elected lane issues)
+        const uint32_t which = (warp == 4) ? 0u : 1u;
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]), ring0 = smem_u32(sB);
+        uint32_t bc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int slice = item % NSL;
 #pragma unroll 1
-                for (int p = 0; p < NP; ++p)
+            for (int p = 0; p < NP; ++p)
 #pragma unroll 1
-                    for (int tap = 0; tap < TAPS; ++tap)
+                for (int tap = 0; tap < TAPS; ++tap)
 #pragma unroll 1
-                        for (int st = 0; st < Cfg::kSub; ++st, ++bc) {
-                            if ((bc & 1u) != which) continue;
-                            const uint32_t slot = bc % S, round = bc / S;
-                            if (round > 0) mbar_wait(&b_empty[slot], (round - 1u) & 1u);
-                            mbar_arrive_expect_tx(&b_full[slot], Cfg::kStageBytes);
+                    for (int st = 0; st < Cfg::kSub; ++st, ++bc) {
+                        if ((bc & 1u) != which) continue;
+                        const uint32_t slot = bc % S, round = bc / S;
+                        if (round > 0) mbar_wait_a(bempty0 + slot * 8u, (round - 1u) & 1u);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx_a(bfull0 + slot * 8u, Cfg::kStageBytes);
                             const int chunk0 = (slice * TAPS + tap) * (NP * KPCH) + p * KPCH + st * (KS / 8);
-                            bulk_g2s(sB + (size_t)slot * Cfg::kStageBytes, Wslab + (size_t)chunk0 * BN * 8,
-                                     Cfg::kStageBytes, &b_full[slot]);
+                            bulk_g2s_a(ring0 + slot * Cfg::kStageBytes, Wslab + (size_t)chunk0 * BN * 8, Cfg::kStageBytes,
+                                       bfull0 + slot * 8u);
                         }
-            }
+                        __syncwarp();
+                    }
         }
-    } else if (warp == 5) {
-        if (lane == 0) {                                               // ---- MMA issuer
-            constexpr uint32_t idesc = idesc_bf16_f32(128, BN);
-            const uint32_t a_base = smem_u32(smem), b_base = smem_u32(sB);
-            uint32_t pc = 0, slot = 0, bphase = 0, it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const uint32_t acc = it & 1u;
-                if (it >= 2) { mbar_wait(&acc_empty[acc], ((it >> 1) - 1u) & 1u); tc_fence_after(); }
-                const uint32_t d_tmem = tmem + acc * BN;
+    } else if (warp == 5) {                                            // ---- MMA issuer (converged warp, elected lane issues:
+        // umma.cuh elect_one -- behind `if (lane == 0)` every tcgen05.mma compiles to an ELECT / R2UR / BRA.U.ANY loop)
+        constexpr uint32_t idesc = idesc_bf16_f32(128, BN);
+        const uint32_t bfull0 = smem_u32(&b_full[0]), bempty0 = smem_u32(&b_empty[0]);
+        const uint32_t afull0 = smem_u32(&a_full[0]), aempty0 = smem_u32(&a_empty[0]);
+        const uint32_t accfull0 = smem_u32(&acc_full[0]), accempty0 = smem_u32(&acc_empty[0]);
+        const uint64_t ad0 = smem_desc(smem_u32(smem) + (uint32_t)(kGuard - DIR * Cfg::kCenter) * 16u, kTcPitch, 128);
+        const uint64_t bd0 = smem_desc(smem_u32(sB), BN * 16u, 128);
+        uint32_t pc = 0, slot = 0, bphase = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u;
+            if (it >= 2) { mbar_wait_a(accempty0 + acc * 8u, ((it >> 1) - 1u) & 1u); tc_fence_after(); }
+            const uint32_t d_tmem = tmem + acc * BN;
 #pragma unroll 1
-                for (int p = 0; p < NP; ++p, ++pc) {
-                    const uint32_t buf = pc & 1u;
-                    if (pc == 0) mbar_wait(&a_first, 0);
-                    else mbar_wait(&a_full[buf], ((pc >> 1) - (buf ^ 1u)) & 1u);   // buffer 0's first fill went through a_first
-                    tc_fence_after();
-                    if (dbg && it < 2 && p == 0) dbg[8 + it * 8] = clock64();
-                    // descriptors advance in 16 B units: one row per tap step, 2 slabs per 16-wide K step
-                    uint64_t a_tap = smem_desc(a_base + buf * Cfg::kPanelBytes +
-                                                   (uint32_t)(kGuard - DIR * Cfg::kCenter) * 16u,
-                                               kTcPitch, 128);
+            for (int p = 0; p < NP; ++p, ++pc) {
+                const uint32_t buf = pc & 1u;
+                if (pc == 0) mbar_wait(&a_first, 0);
+                else mbar_wait_a(afull0 + buf * 8u, ((pc >> 1) - (buf ^ 1u)) & 1u);   // buffer 0's first fill went through a_first
+                tc_fence_after();
+                if (dbg && it < 2 && p == 0 && lane == 0) dbg[8 + it * 8] = clock64();
+                // descriptors advance in 16 B units: one row per tap step, 2 slabs per 16-wide K step
+                uint64_t a_tap = ad0 + (uint64_t)(buf * (Cfg::kPanelBytes / 16));
 #pragma unroll 1
-                    for (int tap = 0; tap < TAPS; ++tap, a_tap += (uint64_t)(int64_t)DIR) {
+                for (int tap = 0; tap < TAPS; ++tap, a_tap += (uint64_t)(int64_t)DIR) {
 #pragma unroll 1
-                        for (int st = 0; st < Cfg::kSub; ++st) {
-                            mbar_wait(&b_full[slot], bphase);
-                            tc_fence_after();
-                            if (dbg && it < 2 && p == 0 && tap == 0 && st == 0) dbg[9 + it * 8] = clock64();
+                    for (int st = 0; st < Cfg::kSub; ++st) {
+                        mbar_wait_a(bfull0 + slot * 8u, bphase);
+                        tc_fence_after();
+                        if (dbg && it < 2 && p == 0 && tap == 0 && st == 0 && lane == 0) dbg[9 + it * 8] = clock64();
+                        if (elect_one()) {
                             const uint64_t ad = a_tap + (uint64_t)(st * (KS / 8) * (kTcPitch / 16));
-                            const uint64_t bd = smem_desc(b_base + slot * Cfg::kStageBytes, BN * 16u, 128);
+                            const uint64_t bd = bd0 + (uint64_t)(slot * (Cfg::kStageBytes / 16));
 #pragma unroll
                             for (int j = 0; j < KS / 16; ++j)
                                 umma_bf16(d_tmem, ad + (uint64_t)(2 * j * (kTcPitch / 16)), bd + (uint64_t)(2 * j * BN),
                                           idesc, (p | tap | st | j) != 0);
-                            umma_commit(&b_empty[slot]);
-                            if (++slot == S) { slot = 0; bphase ^= 1u; }
+                            umma_commit_a(bempty0 + slot * 8u);
                         }
+                        __syncwarp();
+                        if (++slot == S) { slot = 0; bphase ^= 1u; }
                     }
-                    umma_commit(&a_empty[buf]);
                 }
-                umma_commit(&acc_full[acc]);
+                if (elect_one()) umma_commit_a(aempty0 + buf * 8u);
+                __syncwarp();
+            }
+            if (elect_one()) {
+                umma_commit_a(accfull0 + acc * 8u);
                 if (dbg && it < 2) dbg[10 + it * 8] = clock64();
             }
+            __syncwarp();
         }
     } else if (warp >= 8) {                                            // ---- epilogue warps 8..15
         const int q = warp & 3;                                        // TMEM lane quarter this warp may read

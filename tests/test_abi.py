@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import pytest
+
 from glow_tts_b200 import _lib
 from tests._util import REPO
 
@@ -34,6 +36,21 @@ def test_sass_is_sm100a_only(built_lib):
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_gemm_kernels_issue_tcgen05_from_an_elected_lane(built_lib):
+    """The decoder / encoder GEMM kernel and the layer kernel are Blackwell-native (tcgen05.mma, tcgen05.ld, bulk copies)
+    and issue from an elected lane of a converged warp: issued from `if (lane == 0)` the compiler wraps every
+    UTCHMMA / UBLKCP in an ELECT ... BRA.U.ANY loop (umma.cuh: elect_one, profiles/layer_timeline_r02y.md)."""
+    obj = os.path.join(os.path.dirname(built_lib), "_obj", "flow_tc.o")
+    if not os.path.exists(obj):
+        pytest.skip("object files not kept")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "tc_layer_kernel" in sass and "tc_gemm3_kernel" in sass
+    for mnemonic in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "ENL2.256" in sass                      # the layer kernel's one-row-per-thread 256-bit global accesses
+    assert "BRA.U.ANY" not in sass
 
 
 def test_product_never_imports_oracle():
